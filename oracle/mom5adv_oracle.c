@@ -1,0 +1,871 @@
+/*
+ * mom5adv_oracle.c -- CPU ORACLE (test infrastructure; see mom5adv_oracle.h header comment).
+ *
+ * Every loop nest below cites the reference lines it restates.
+ *   OTA  = /root/reference/src/mom5/ocean_tracers/ocean_tracer_advect.F90
+ *   MPPI = /root/reference/src/shared/mpp/include
+ * Expression trees are written with explicit parentheses that reproduce Fortran's
+ * left-to-right evaluation of equal-precedence operators.  Compile WITHOUT FMA contraction.
+ */
+#include "mom5adv_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ONESIXTH (1.0 / 6.0) /* ocean_parameters.F90:92 */
+
+/* max/min: first argument wins ties (and is kept when the second is NaN); inputs are NaN-free. */
+static inline double orc_max(double a, double b) { return (b > a) ? b : a; }
+static inline double orc_min(double a, double b) { return (b < a) ? b : a; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* index helpers (Fortran indices: i in isd..ied etc.; k 1-based) */
+#define NX1(b) ((b)->ni + 2)
+#define NY1(b) ((b)->nj + 2)
+#define NX2(b) ((b)->ni + 4)
+#define NY2(b) ((b)->nj + 4)
+#define D2(b, i, j) ((size_t)(i) + (size_t)NX1(b) * (size_t)(j))
+#define D3(b, i, j, k) ((size_t)(i) + (size_t)NX1(b) * ((size_t)(j) + (size_t)NY1(b) * (size_t)((k)-1)))
+#define W3(b, i, j, k) ((size_t)(i) + (size_t)NX1(b) * ((size_t)(j) + (size_t)NY1(b) * (size_t)(k))) /* k = 0..nk */
+#define H2(b, i, j) ((size_t)((i) + 1) + (size_t)NX2(b) * (size_t)((j) + 1))
+#define H3(b, i, j, k) ((size_t)((i) + 1) + (size_t)NX2(b) * ((size_t)((j) + 1) + (size_t)NY2(b) * (size_t)((k)-1)))
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout: mpp_define_layout2D (MPPI/mpp_domains_define.inc:28-55)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_define_layout(int ni_g, int nj_g, int ndivs, int *layout2)
+{
+    int isz = ni_g, jsz = nj_g;
+    /* idiv = nint( sqrt(float(ndivs*isz)/jsz) ) : float() is default real; -r8 builds make it binary64 */
+    double q = (double)((long)ndivs * (long)isz) / (double)jsz;
+    int idiv = (int)lround(sqrt(q));
+    idiv = imax(idiv, 1);
+    while (ndivs % idiv != 0) idiv--;
+    layout2[0] = idiv;
+    layout2[1] = ndivs / idiv;
+}
+
+/* mpp_compute_extent (MPPI/mpp_domains_define.inc:187-273), no user extent. Returns 0 on success. */
+int orc_compute_extent(int isg, int ieg, int ndivs, int *ibegin, int *iend)
+{
+    int npts = ieg - isg + 1;
+    int even_n = (ndivs % 2 == 0), even_p = (npts % 2 == 0);
+    int symmetrize = (even_n && even_p) || (!even_n && !even_p) || (!even_n && even_p && ndivs < npts / 2);
+    int is = isg, ie = 0, imaxv = ieg, ndmax = ndivs;
+    for (int ndiv = 0; ndiv < ndivs; ndiv++) {
+        if (ndiv < (ndivs - 1) / 2 + 1) {
+            ie = is + (int)ceil((double)(imaxv - is + 1) / (double)(ndmax - ndiv)) - 1;
+            int ndmirror = (ndivs - 1) - ndiv;
+            if (ndmirror > ndiv && symmetrize) {
+                ibegin[ndmirror] = imax(isg + ieg - ie, ie + 1);
+                iend[ndmirror] = imax(isg + ieg - is, ie + 1);
+                imaxv = ibegin[ndmirror] - 1;
+                ndmax = ndmax - 1;
+            }
+        } else {
+            if (symmetrize) {
+                is = ibegin[ndiv];
+                ie = iend[ndiv];
+            } else {
+                ie = is + (int)ceil((double)(imaxv - is + 1) / (double)(ndmax - ndiv)) - 1;
+            }
+        }
+        ibegin[ndiv] = is;
+        iend[ndiv] = ie;
+        if (ie < is) return 1;
+        if (ndiv == ndivs - 1 && iend[ndiv] != ieg) return 2;
+        is = ie + 1;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Halo update among in-process blocks.
+ * Semantics (scalar field at CENTER position):
+ *   - interior neighbour / cyclic wrap: plain copy                         (MPPI/mpp_do_update.h:186-293)
+ *   - folded north edge: (i, nj_g+m) <- (ni_g+1-i, nj_g+1-m), no sign      (MPPI/mpp_domains_define.inc:4865-4885,
+ *                                                                            test_mpp_domains.F90:3749-3766)
+ *   - solid wall: halo left untouched                                      (no overlap is generated)
+ *   - XUPDATE: E/W strips, j in compute domain only; YUPDATE: N/S strips, i in compute only;
+ *     both: all eight directions                                           (MPPI/mpp_do_update.h:57-78)
+ * ---------------------------------------------------------------------------------------------- */
+static int find_div(const int *beg, const int *end, int n, int g)
+{
+    for (int d = 0; d < n; d++)
+        if (g >= beg[d] && g <= end[d]) return d;
+    return -1;
+}
+
+/* map a global (possibly out-of-range) point to its source global compute point; 0 if none (wall) */
+static int map_source(const orc_layout *L, int ig, int jg, int *igs, int *jgs)
+{
+    if (jg > L->nj_g) {
+        if (L->fold_north) {
+            jg = 2 * L->nj_g + 1 - jg;
+            ig = L->ni_g + 1 - ig;
+        } else if (L->cyclic_y) {
+            jg -= L->nj_g;
+        } else
+            return 0;
+    } else if (jg < 1) {
+        if (L->cyclic_y)
+            jg += L->nj_g;
+        else
+            return 0;
+    }
+    if (ig < 1) {
+        if (!L->cyclic_x) return 0;
+        ig += L->ni_g;
+    } else if (ig > L->ni_g) {
+        if (!L->cyclic_x) return 0;
+        ig -= L->ni_g;
+    }
+    if (ig < 1 || ig > L->ni_g || jg < 1 || jg > L->nj_g) return 0;
+    *igs = ig;
+    *jgs = jg;
+    return 1;
+}
+
+void orc_update_halo(const orc_layout *L, double *const *fields, int nk, int halo, int flags)
+{
+    int nb = L->px * L->py;
+    /* Two-phase (gather into per-block staging, then write) so that a block's halo never feeds another
+     * block's halo within one update -- sources are compute-domain points only, so single phase is safe:
+     * halo cells are written, compute cells are read, the two sets are disjoint. */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int b = 0; b < nb; b++) {
+        int bx = b % L->px, by = b / L->px;
+        int ni = L->iend[bx] - L->ibeg[bx] + 1, nj = L->jend[by] - L->jbeg[by] + 1;
+        int nxh = ni + 2 * halo, nyh = nj + 2 * halo;
+        double *dst = fields[b];
+        for (int jl = 1 - halo; jl <= nj + halo; jl++) {
+            int j_in = (jl >= 1 && jl <= nj);
+            for (int il = 1 - halo; il <= ni + halo; il++) {
+                int i_in = (il >= 1 && il <= ni);
+                if (i_in && j_in) { il = ni; continue; } /* skip the compute domain */
+                int want;
+                if (!i_in && j_in)
+                    want = flags & ORC_XUPDATE;
+                else if (i_in && !j_in)
+                    want = flags & ORC_YUPDATE;
+                else
+                    want = (flags & ORC_XUPDATE) && (flags & ORC_YUPDATE);
+                if (!want) continue;
+                int igs, jgs;
+                if (!map_source(L, L->ibeg[bx] + il - 1, L->jbeg[by] + jl - 1, &igs, &jgs)) continue;
+                int sx = find_div(L->ibeg, L->iend, L->px, igs), sy = find_div(L->jbeg, L->jend, L->py, jgs);
+                int sni = L->iend[sx] - L->ibeg[sx] + 1, snj = L->jend[sy] - L->jbeg[sy] + 1;
+                int snxh = sni + 2 * halo, snyh = snj + 2 * halo;
+                const double *src = fields[sx + L->px * sy];
+                int isl = igs - L->ibeg[sx] + 1, jsl = jgs - L->jbeg[sy] + 1;
+                size_t so = (size_t)(isl - 1 + halo) + (size_t)snxh * (size_t)(jsl - 1 + halo);
+                size_t dofs = (size_t)(il - 1 + halo) + (size_t)nxh * (size_t)(jl - 1 + halo);
+                for (int k = 0; k < nk; k++)
+                    dst[dofs + (size_t)nxh * nyh * k] = src[so + (size_t)snxh * snyh * k];
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * mdfl_init: tmask_mdfl = 0; compute domain := Grd%tmask (OTA:1660-1674); halo update by caller (OTA:1675)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_mdfl_init_mask(const orc_block *b)
+{
+    memset(b->tmask_h2, 0, sizeof(double) * (size_t)NX2(b) * NY2(b) * b->nk);
+    for (int k = 1; k <= b->nk; k++)
+        for (int j = 1; j <= b->nj; j++)
+            for (int i = 1; i <= b->ni; i++) b->tmask_h2[H3(b, i, j, k)] = b->tmask[D3(b, i, j, k)];
+}
+
+/* shared Sweby limiter block (OTA:4174-4189 == 4266-4281 == 4377-4392), see SURVEY.md Appendix A.1 */
+static inline double sweby_flux(double Rjp, double Rj, double Rjm, double massflux, double cfl, double Tup,
+                                double Tdn, double mA, double mB)
+{
+    double d0 = ((2.0 - cfl) * (1.0 - cfl)) * ONESIXTH;
+    double d1 = (1.0 - (cfl * cfl)) * ONESIXTH;
+    double thetaP = Rjm / (1.0e-30 + Rj);
+    double thetaM = Rjp / (1.0e-30 + Rj);
+    double psiP = orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaP)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaP));
+    double psiM = orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaM)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaM));
+    return ((0.5 * (((massflux + fabs(massflux)) * (Tup + (psiP * Rj))) +
+                    ((massflux - fabs(massflux)) * (Tdn - (psiM * Rj))))) *
+            mA) *
+           mB;
+}
+
+/* a2 variant: psi = psi_lin*(1-sl) + psi_lim*sl (OTA:3874-3884) */
+static inline double sweby_flux_sl(double Rjp, double Rj, double Rjm, double massflux, double cfl, double Tup,
+                                   double Tdn, double mA, double mB, double sl)
+{
+    double d0 = ((2.0 - cfl) * (1.0 - cfl)) * ONESIXTH;
+    double d1 = (1.0 - (cfl * cfl)) * ONESIXTH;
+    double thetaP = Rjm / (1.0e-30 + Rj);
+    double thetaM = Rjp / (1.0e-30 + Rj);
+    double psiP = d0 + (d1 * thetaP);
+    psiP = (psiP * (1.0 - sl)) +
+           (orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaP)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaP)) * sl);
+    double psiM = d0 + (d1 * thetaM);
+    psiM = (psiM * (1.0 - sl)) +
+           (orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaM)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaM)) * sl);
+    return ((0.5 * (((massflux + fabs(massflux)) * (Tup + (psiP * Rj))) +
+                    ((massflux - fabs(massflux)) * (Tdn - (psiM * Rj))))) *
+            mA) *
+           mB;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * advect_tracer_sweby_all, z sweep (OTA:4136-4211)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_sweby_all_z(const orc_block *b, int ntr, double dtime, const double *const *T, const double *w,
+                     const double *rho, double *const *tm, double *const *flux_z, double *const *adv_z)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *ftp = (double *)malloc(sizeof(double) * (size_t)ni * nj);
+    double *wkm1 = (double *)malloc(sizeof(double) * (size_t)ni * nj);
+    for (int n = 0; n < ntr; n++) {
+        const double *Tn = T[n];
+        double *tmn = tm[n];
+        for (size_t q = 0; q < (size_t)ni * nj; q++) { ftp[q] = 0.0; wkm1[q] = 0.0; } /* OTA:4138-4140 */
+        for (int k = 1; k <= nk; k++) {
+            int kp1 = imin(k + 1, nk), kp2 = imin(k + 2, nk), km1 = imax(k - 1, 1);
+            for (int j = 1; j <= nj; j++)
+                for (int i = 1; i <= ni; i++) {
+                    size_t c = (size_t)(i - 1) + (size_t)ni * (j - 1);
+                    double Tk = Tn[D3(b, i, j, k)], Tkp1 = Tn[D3(b, i, j, kp1)];
+                    double Rjp = ((Tn[D3(b, i, j, km1)] - Tk) * m[H3(b, i, j, km1)]) * m[H3(b, i, j, k)];
+                    double Rj = ((Tk - Tkp1) * m[H3(b, i, j, k)]) * m[H3(b, i, j, kp1)];
+                    double Rjm = ((Tkp1 - Tn[D3(b, i, j, kp2)]) * m[H3(b, i, j, kp1)]) * m[H3(b, i, j, kp2)];
+                    double wk = w[W3(b, i, j, k)], r = rho[D3(b, i, j, k)];
+                    double massflux = b->dat[D2(b, i, j)] * wk;
+                    double cfl = fabs((wk * dtime) / r);
+                    double fbt = sweby_flux(Rjp, Rj, Rjm, massflux, cfl, Tkp1, Tk, m[H3(b, i, j, kp1)], m[H3(b, i, j, k)]);
+                    double wz = (b->datr[D2(b, i, j)] * (fbt - ftp[c])) + (Tk * (wkm1[c] - wk));  /* OTA:4191-4192 */
+                    tmn[H3(b, i, j, k)] = Tk + ((wz * dtime) / r);                               /* OTA:4154,4194-4195 */
+                    if (flux_z && flux_z[n]) flux_z[n][D3(b, i, j, k)] = fbt;
+                    if (adv_z && adv_z[n]) adv_z[n][D3(b, i, j, k)] = wz;
+                    ftp[c] = fbt;
+                }
+            for (int j = 1; j <= nj; j++) /* OTA:4205-4209 */
+                for (int i = 1; i <= ni; i++) wkm1[(size_t)(i - 1) + (size_t)ni * (j - 1)] = w[W3(b, i, j, k)];
+        }
+    }
+    free(ftp);
+    free(wkm1);
+}
+
+/* x sweep (OTA:4243-4300) */
+void orc_sweby_all_x(const orc_block *b, int ntr, double dtime, const double *const *T, const double *u,
+                     const double *rho, double *const *tm, double *const *flux_x, double *const *adv_x)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *fx = (double *)malloc(sizeof(double) * (size_t)(ni + 1)); /* faces i = 0..ni of one row */
+    for (int n = 0; n < ntr; n++) {
+        const double *Tn = T[n];
+        double *tmn = tm[n];
+        for (int k = 1; k <= nk; k++)
+            for (int j = 1; j <= nj; j++) {
+                for (int i = 0; i <= ni; i++) { /* OTA:4254-4282 */
+                    double t0 = tmn[H3(b, i, j, k)], t1 = tmn[H3(b, i + 1, j, k)];
+                    double Rjp = ((tmn[H3(b, i + 2, j, k)] - t1) * m[H3(b, i + 2, j, k)]) * m[H3(b, i + 1, j, k)];
+                    double Rj = ((t1 - t0) * m[H3(b, i + 1, j, k)]) * m[H3(b, i, j, k)];
+                    double Rjm = ((t0 - tmn[H3(b, i - 1, j, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i - 1, j, k)];
+                    double uu = u[D3(b, i, j, k)];
+                    double massflux = b->dyte[D2(b, i, j)] * uu;
+                    double cfl = fabs(((uu * dtime) * 2.0) /
+                                      ((rho[D3(b, i, j, k)] + rho[D3(b, i + 1, j, k)]) * b->dxte[D2(b, i, j)]));
+                    fx[i] = sweby_flux(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i + 1, j, k)]);
+                    if (flux_x && flux_x[n]) flux_x[n][D3(b, i, j, k)] = fx[i];
+                }
+                for (int i = 1; i <= ni; i++) { /* OTA:4286-4296 */
+                    double wx = (m[H3(b, i, j, k)] * b->datr[D2(b, i, j)]) *
+                                ((fx[i - 1] - fx[i]) +
+                                 (Tn[D3(b, i, j, k)] * ((b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)]) -
+                                                       (b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)]))));
+                    tmn[H3(b, i, j, k)] = tmn[H3(b, i, j, k)] + ((wx * dtime) / rho[D3(b, i, j, k)]);
+                    if (adv_x && adv_x[n]) adv_x[n][D3(b, i, j, k)] = wx;
+                }
+            }
+    }
+    free(fx);
+}
+
+/* y sweep + total tendency (OTA:4347-4432) */
+void orc_sweby_all_y(const orc_block *b, int ntr, double dtime, const double *const *T, const double *u,
+                     const double *v, const double *w, const double *rho, double *const *tm,
+                     double *const *th, double *const *adv, double *const *flux_y, double *const *adv_y)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *fy = (double *)malloc(sizeof(double) * (size_t)ni * (nj + 1)); /* faces j = 0..nj */
+    for (int n = 0; n < ntr; n++) {
+        const double *Tn = T[n];
+        double *tmn = tm[n];
+        /* T_prog(n)%wrk1 zeroed over the whole data domain (OTA:4142-4148) */
+        memset(adv[n], 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk);
+        for (int k = 1; k <= nk; k++) {
+            for (int j = 0; j <= nj; j++) /* OTA:4364-4395 */
+                for (int i = 1; i <= ni; i++) {
+                    double t0 = tmn[H3(b, i, j, k)], t1 = tmn[H3(b, i, j + 1, k)];
+                    double Rjp = ((tmn[H3(b, i, j + 2, k)] - t1) * m[H3(b, i, j + 2, k)]) * m[H3(b, i, j + 1, k)];
+                    double Rj = ((t1 - t0) * m[H3(b, i, j + 1, k)]) * m[H3(b, i, j, k)];
+                    double Rjm = ((t0 - tmn[H3(b, i, j - 1, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i, j - 1, k)];
+                    double vv = v[D3(b, i, j, k)];
+                    double massflux = b->dxtn[D2(b, i, j)] * vv;
+                    double cfl = fabs(((vv * dtime) * 2.0) /
+                                      ((rho[D3(b, i, j, k)] + rho[D3(b, i, j + 1, k)]) * b->dytn[D2(b, i, j)]));
+                    double f = sweby_flux(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i, j + 1, k)]);
+                    fy[(size_t)(i - 1) + (size_t)ni * j] = f;
+                    if (flux_y && flux_y[n]) flux_y[n][D3(b, i, j, k)] = f;
+                }
+            for (int j = 1; j <= nj; j++) /* OTA:4398-4424 */
+                for (int i = 1; i <= ni; i++) {
+                    double Tk = Tn[D3(b, i, j, k)], r = rho[D3(b, i, j, k)];
+                    double wkm1 = (k == 1) ? 0.0 : w[W3(b, i, j, k - 1)]; /* OTA:4356-4360, 4427-4431 */
+                    double wy = ((m[H3(b, i, j, k)] * b->datr[D2(b, i, j)]) *
+                                 (fy[(size_t)(i - 1) + (size_t)ni * (j - 1)] - fy[(size_t)(i - 1) + (size_t)ni * j])) +
+                                (Tk * ((w[W3(b, i, j, k)] - wkm1) +
+                                       (b->datr[D2(b, i, j)] * ((b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)]) -
+                                                                (b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)])))));
+                    double t = tmn[H3(b, i, j, k)] + ((wy * dtime) / r);
+                    tmn[H3(b, i, j, k)] = t;
+                    double a = ((r * (t - Tk)) / dtime) * m[H3(b, i, j, k)];
+                    adv[n][D3(b, i, j, k)] = a;
+                    th[n][D3(b, i, j, k)] = th[n][D3(b, i, j, k)] + a;
+                    if (adv_y && adv_y[n]) adv_y[n][D3(b, i, j, k)] = wy;
+                }
+        }
+    }
+    free(fy);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * advect_tracer_mdfl_sweby (OTA:3806-4066)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_mdfl_sweby_z(const orc_block *b, double dtime, double sl, const double *T, const double *w,
+                      const double *rho, double *tm, double *flux_z)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *ftp = (double *)calloc((size_t)ni * nj, sizeof(double));
+    double *wkm1 = (double *)calloc((size_t)ni * nj, sizeof(double));
+    memset(tm, 0, sizeof(double) * (size_t)NX2(b) * NY2(b) * nk); /* tracer_mdfl = 0.0 (OTA:3836) */
+    for (int k = 1; k <= nk; k++) {
+        int kp1 = imin(k + 1, nk), kp2 = imin(k + 2, nk), km1 = imax(k - 1, 1);
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t c = (size_t)(i - 1) + (size_t)ni * (j - 1);
+                double Tk = T[D3(b, i, j, k)], Tkp1 = T[D3(b, i, j, kp1)];
+                double Rjp = ((T[D3(b, i, j, km1)] - Tk) * m[H3(b, i, j, km1)]) * m[H3(b, i, j, k)];
+                double Rj = ((Tk - Tkp1) * m[H3(b, i, j, k)]) * m[H3(b, i, j, kp1)];
+                double Rjm = ((Tkp1 - T[D3(b, i, j, kp2)]) * m[H3(b, i, j, kp1)]) * m[H3(b, i, j, kp2)];
+                double wk = w[W3(b, i, j, k)], r = rho[D3(b, i, j, k)];
+                double massflux = b->dat[D2(b, i, j)] * wk;
+                double cfl = fabs((wk * dtime) / r);
+                double fbt = sweby_flux_sl(Rjp, Rj, Rjm, massflux, cfl, Tkp1, Tk, m[H3(b, i, j, kp1)], m[H3(b, i, j, k)], sl);
+                /* OTA:3892-3896 */
+                tm[H3(b, i, j, k)] = Tk + ((dtime / r) * ((b->datr[D2(b, i, j)] * (fbt - ftp[c])) + (Tk * (wkm1[c] - wk))));
+                if (flux_z) flux_z[D3(b, i, j, k)] = fbt;
+                ftp[c] = fbt;
+            }
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) wkm1[(size_t)(i - 1) + (size_t)ni * (j - 1)] = w[W3(b, i, j, k)];
+    }
+    free(ftp);
+    free(wkm1);
+}
+
+void orc_mdfl_sweby_x(const orc_block *b, double dtime, double sl, const double *T, const double *u,
+                      const double *rho, double *tm, double *flux_x)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *fx = (double *)malloc(sizeof(double) * (size_t)(ni + 1));
+    if (flux_x) memset(flux_x, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk); /* OTA:3837 */
+    for (int k = 1; k <= nk; k++)
+        for (int j = 1; j <= nj; j++) {
+            for (int i = 0; i <= ni; i++) { /* OTA:3918-3955 */
+                double t0 = tm[H3(b, i, j, k)], t1 = tm[H3(b, i + 1, j, k)];
+                double Rjp = ((tm[H3(b, i + 2, j, k)] - t1) * m[H3(b, i + 2, j, k)]) * m[H3(b, i + 1, j, k)];
+                double Rj = ((t1 - t0) * m[H3(b, i + 1, j, k)]) * m[H3(b, i, j, k)];
+                double Rjm = ((t0 - tm[H3(b, i - 1, j, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i - 1, j, k)];
+                double uu = u[D3(b, i, j, k)];
+                double massflux = b->dyte[D2(b, i, j)] * uu;
+                double cfl = fabs(((uu * dtime) * 2.0) /
+                                  ((rho[D3(b, i, j, k)] + rho[D3(b, i + 1, j, k)]) * b->dxte[D2(b, i, j)]));
+                fx[i] = sweby_flux_sl(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i + 1, j, k)], sl);
+                if (flux_x) flux_x[D3(b, i, j, k)] = fx[i];
+            }
+            for (int i = 1; i <= ni; i++) { /* OTA:3958-3967 */
+                double coef = ((dtime * m[H3(b, i, j, k)]) * b->datr[D2(b, i, j)]) / rho[D3(b, i, j, k)];
+                tm[H3(b, i, j, k)] =
+                    tm[H3(b, i, j, k)] +
+                    (coef * ((fx[i - 1] - fx[i]) +
+                             (T[D3(b, i, j, k)] * ((b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)]) -
+                                                   (b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)])))));
+            }
+        }
+    free(fx);
+}
+
+void orc_mdfl_sweby_y(const orc_block *b, double dtime, double sl, const double *T, const double *u,
+                      const double *v, const double *w, const double *rho, double *tm, double *flux_y,
+                      double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    double *fy = (double *)malloc(sizeof(double) * (size_t)ni * (nj + 1));
+    if (flux_y) memset(flux_y, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk); /* OTA:3838 */
+    memset(wrk1_out, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk);           /* OTA:1925-1931 */
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 0; j <= nj; j++) /* OTA:3982-4020 */
+            for (int i = 1; i <= ni; i++) {
+                double t0 = tm[H3(b, i, j, k)], t1 = tm[H3(b, i, j + 1, k)];
+                double Rjp = ((tm[H3(b, i, j + 2, k)] - t1) * m[H3(b, i, j + 2, k)]) * m[H3(b, i, j + 1, k)];
+                double Rj = ((t1 - t0) * m[H3(b, i, j + 1, k)]) * m[H3(b, i, j, k)];
+                double Rjm = ((t0 - tm[H3(b, i, j - 1, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i, j - 1, k)];
+                double vv = v[D3(b, i, j, k)];
+                double massflux = b->dxtn[D2(b, i, j)] * vv;
+                double cfl = fabs(((vv * dtime) * 2.0) /
+                                  ((rho[D3(b, i, j, k)] + rho[D3(b, i, j + 1, k)]) * b->dytn[D2(b, i, j)]));
+                double f = sweby_flux_sl(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i, j + 1, k)], sl);
+                fy[(size_t)(i - 1) + (size_t)ni * j] = f;
+                if (flux_y) flux_y[D3(b, i, j, k)] = f;
+            }
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                double Tk = T[D3(b, i, j, k)], r = rho[D3(b, i, j, k)];
+                double wkm1 = (k == 1) ? 0.0 : w[W3(b, i, j, k - 1)];
+                /* OTA:4025-4027 */
+                double t = tm[H3(b, i, j, k)] +
+                           ((((dtime * m[H3(b, i, j, k)]) * b->datr[D2(b, i, j)]) / r) *
+                            (fy[(size_t)(i - 1) + (size_t)ni * (j - 1)] - fy[(size_t)(i - 1) + (size_t)ni * j]));
+                /* OTA:4035-4040 */
+                t = t + (((dtime * Tk) / r) *
+                         ((w[W3(b, i, j, k)] - wkm1) +
+                          (b->datr[D2(b, i, j)] * ((b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)]) -
+                                                   (b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)])))));
+                tm[H3(b, i, j, k)] = t;
+                /* function value = -(rho*(tm-T)/dtime*m) (OTA:4043-4045); caller stores wrk1 = -value (OTA:1958-1959) */
+                double fval = -(((r * (t - Tk)) / dtime) * m[H3(b, i, j, k)]);
+                wrk1_out[D3(b, i, j, k)] = -fval;
+            }
+    }
+    free(fy);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * quicker_init (OTA:1442-1586)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_quicker_init_pre(const orc_block *b)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    memset(b->tmask_h2, 0, sizeof(double) * (size_t)NX2(b) * NY2(b) * nk);
+    memset(b->dxt_h2, 0, sizeof(double) * (size_t)NX2(b) * NY2(b));
+    memset(b->dyt_h2, 0, sizeof(double) * (size_t)NX2(b) * NY2(b));
+    for (int i = 1; i <= ni; i++) /* OTA:1478-1486 */
+        for (int j = 1; j <= nj; j++) {
+            b->dxt_h2[H2(b, i, j)] = b->dxt[D2(b, i, j)];
+            b->dyt_h2[H2(b, i, j)] = b->dyt[D2(b, i, j)];
+            for (int k = 1; k <= nk; k++) b->tmask_h2[H3(b, i, j, k)] = b->tmask[D3(b, i, j, k)];
+        }
+}
+
+void orc_quicker_init_edges(const orc_block *b)
+{
+    const int ni = b->ni, nj = b->nj;
+    double *dx = b->dxt_h2, *dy = b->dyt_h2;
+    for (int i = -1; i <= 0; i++) { /* OTA:1491-1494 */
+        for (int j = 1; j <= nj; j++) dx[H2(b, i, j)] = dx[H2(b, 1, j)];
+        for (int j = -1; j <= nj + 2; j++) dy[H2(b, i, j)] = dy[H2(b, 1, j)];
+    }
+    for (int i = ni + 1; i <= ni + 2; i++) { /* OTA:1496-1499 */
+        for (int j = 1; j <= nj; j++) dx[H2(b, i, j)] = dx[H2(b, ni, j)];
+        for (int j = -1; j <= nj + 2; j++) dy[H2(b, i, j)] = dy[H2(b, ni, j)];
+    }
+    for (int j = -1; j <= 0; j++) /* OTA:1501-1504 */
+        for (int i = -1; i <= ni + 2; i++) {
+            dx[H2(b, i, j)] = dx[H2(b, i, 1)];
+            dy[H2(b, i, j)] = dy[H2(b, i, 1)];
+        }
+    for (int j = nj + 1; j <= nj + 2; j++) /* OTA:1506-1509 */
+        for (int i = -1; i <= ni + 2; i++) {
+            dx[H2(b, i, j)] = dx[H2(b, i, nj)];
+            dy[H2(b, i, j)] = dy[H2(b, i, nj)];
+        }
+}
+
+#define Q2(b, i, j, c) ((size_t)(i) + (size_t)NX1(b) * ((size_t)(j) + (size_t)NY1(b) * (size_t)((c)-1)))
+
+void orc_quicker_init_weights(const orc_block *b)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *dx = b->dxt_h2, *dy = b->dyt_h2;
+    size_t n2 = (size_t)NX1(b) * NY1(b);
+    memset(b->quick_x, 0, sizeof(double) * n2 * 2);
+    memset(b->quick_y, 0, sizeof(double) * n2 * 2);
+    memset(b->curv_xp, 0, sizeof(double) * n2 * 3);
+    memset(b->curv_xn, 0, sizeof(double) * n2 * 3);
+    memset(b->curv_yp, 0, sizeof(double) * n2 * 3);
+    memset(b->curv_yn, 0, sizeof(double) * n2 * 3);
+    for (int i = 0; i <= ni; i++) /* OTA:1516-1564 */
+        for (int j = 0; j <= nj; j++) {
+            double xm = dx[H2(b, i - 1, j)], x0 = dx[H2(b, i, j)], x1 = dx[H2(b, i + 1, j)], x2 = dx[H2(b, i + 2, j)];
+            double ym = dy[H2(b, i, j - 1)], y0 = dy[H2(b, i, j)], y1 = dy[H2(b, i, j + 1)], y2 = dy[H2(b, i, j + 2)];
+            b->quick_x[Q2(b, i, j, 1)] = x1 / (x1 + x0);
+            b->quick_x[Q2(b, i, j, 2)] = x0 / (x1 + x0);
+            b->quick_y[Q2(b, i, j, 1)] = y1 / (y1 + y0);
+            b->quick_y[Q2(b, i, j, 2)] = y0 / (y1 + y0);
+
+            b->curv_xp[Q2(b, i, j, 1)] = (x0 * x1) / (((xm + (2.0 * x0)) + x1) * (x0 + x1));
+            b->curv_xp[Q2(b, i, j, 2)] = -((x0 * x1) / ((x0 + x1) * (xm + x0)));
+            b->curv_xp[Q2(b, i, j, 3)] = (x0 * x1) / (((xm + (2.0 * x0)) + x1) * (xm + x0));
+
+            b->curv_xn[Q2(b, i, j, 1)] = (x0 * x1) / (((x0 + (2.0 * x1)) + x2) * (x1 + x2));
+            b->curv_xn[Q2(b, i, j, 2)] = -((x0 * x1) / ((x1 + x2) * (x0 + x1)));
+            b->curv_xn[Q2(b, i, j, 3)] = (x0 * x1) / (((x0 + (2.0 * x1)) + x2) * (x0 + x1));
+
+            b->curv_yp[Q2(b, i, j, 1)] = (y0 * y1) / (((ym + (2.0 * y0)) + y1) * (y0 + y1));
+            b->curv_yp[Q2(b, i, j, 2)] = -((y0 * y1) / ((y0 + y1) * (ym + y0)));
+            b->curv_yp[Q2(b, i, j, 3)] = (y0 * y1) / (((ym + (2.0 * y0)) + y1) * (ym + y0));
+
+            b->curv_yn[Q2(b, i, j, 1)] = (y0 * y1) / (((y0 + (2.0 * y1)) + y2) * (y1 + y2));
+            b->curv_yn[Q2(b, i, j, 2)] = -((y0 * y1) / ((y1 + y2) * (y0 + y1)));
+            b->curv_yn[Q2(b, i, j, 3)] = (y0 * y1) / (((y0 + (2.0 * y1)) + y2) * (y0 + y1));
+        }
+    for (int k = 1; k <= nk; k++) { /* OTA:1566-1578 ; quick_z(k,c) at (k-1) + nk*(c-1) */
+        int kp2 = imin(k + 2, nk), kp1 = imin(k + 1, nk), km1 = imax(k - 1, 1);
+        double zm = b->dzt[km1 - 1], z0 = b->dzt[k - 1], z1 = b->dzt[kp1 - 1], z2 = b->dzt[kp2 - 1];
+        b->quick_z[(k - 1) + nk * 0] = z1 / (z1 + z0);
+        b->quick_z[(k - 1) + nk * 1] = z0 / (z1 + z0);
+        b->curv_zp[(k - 1) + nk * 0] = (z0 * z1) / (((zm + (2.0 * z0)) + z1) * (z0 + z1));
+        b->curv_zp[(k - 1) + nk * 1] = -((z0 * z1) / ((z0 + z1) * (zm + z0)));
+        b->curv_zp[(k - 1) + nk * 2] = (z0 * z1) / (((zm + (2.0 * z0)) + z1) * (zm + z0));
+        b->curv_zn[(k - 1) + nk * 0] = (z0 * z1) / (((z0 + (2.0 * z1)) + z2) * (z1 + z2));
+        b->curv_zn[(k - 1) + nk * 1] = -((z0 * z1) / ((z1 + z2) * (z0 + z1)));
+        b->curv_zn[(k - 1) + nk * 2] = (z0 * z1) / (((z0 + (2.0 * z1)) + z2) * (z0 + z1));
+    }
+}
+
+/* tracer_quick = 0; compute domain := T(taum1) (OTA:2558-2565); full halo update by caller (OTA:2566) */
+void orc_quicker_prep(const orc_block *b, const double *T_taum1, double *tq)
+{
+    memset(tq, 0, sizeof(double) * (size_t)NX2(b) * NY2(b) * b->nk);
+    for (int k = 1; k <= b->nk; k++)
+        for (int j = 1; j <= b->nj; j++)
+            for (int i = 1; i <= b->ni; i++) tq[H3(b, i, j, k)] = T_taum1[D3(b, i, j, k)];
+}
+
+/* OTA:2568-2637 */
+void orc_horz_quicker_flux(const orc_block *b, const double *Tm1, const double *Tt, const double *tq,
+                           const double *u, const double *v, const double *tmask_limit, int limit_with_upwind,
+                           double *flux_x, double *flux_y)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *mq = b->tmask_h2;
+    memset(flux_x, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk);
+    memset(flux_y, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk);
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 0; j <= nj; j++) /* OTA:2572-2588 */
+            for (int i = 1; i <= ni; i++) {
+                double vel = b->dxtn[D2(b, i, j)] * v[D3(b, i, j, k)];
+                double upos = 0.5 * (vel + fabs(vel));
+                double uneg = 0.5 * (vel - fabs(vel));
+                double rnormsk = mq[H3(b, i, j, k)] * (1.0 - mq[H3(b, i, j - 1, k)]);
+                double soutmsk = mq[H3(b, i, j + 1, k)] * (1.0 - mq[H3(b, i, j + 2, k)]);
+                double t0 = tq[H3(b, i, j, k)], t1 = tq[H3(b, i, j + 1, k)];
+                flux_y[D3(b, i, j, k)] =
+                    ((vel * ((b->quick_y[Q2(b, i, j, 1)] * Tt[D3(b, i, j, k)]) +
+                             (b->quick_y[Q2(b, i, j, 2)] * Tt[D3(b, i, j + 1, k)]))) -
+                     (upos * (((b->curv_yp[Q2(b, i, j, 1)] * t1) + (b->curv_yp[Q2(b, i, j, 2)] * t0)) +
+                              (b->curv_yp[Q2(b, i, j, 3)] * ((tq[H3(b, i, j - 1, k)] * (1.0 - rnormsk)) + (t0 * rnormsk)))))) -
+                    (uneg * (((b->curv_yn[Q2(b, i, j, 1)] * ((tq[H3(b, i, j + 2, k)] * (1.0 - soutmsk)) + (t1 * soutmsk))) +
+                              (b->curv_yn[Q2(b, i, j, 2)] * t1)) +
+                             (b->curv_yn[Q2(b, i, j, 3)] * t0)));
+            }
+        for (int j = 1; j <= nj; j++) /* OTA:2590-2606 */
+            for (int i = 0; i <= ni; i++) {
+                double vel = b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)];
+                double upos = 0.5 * (vel + fabs(vel));
+                double uneg = 0.5 * (vel - fabs(vel));
+                double eastmsk = mq[H3(b, i, j, k)] * (1.0 - mq[H3(b, i - 1, j, k)]);
+                double westmsk = mq[H3(b, i + 1, j, k)] * (1.0 - mq[H3(b, i + 2, j, k)]);
+                double t0 = tq[H3(b, i, j, k)], t1 = tq[H3(b, i + 1, j, k)];
+                flux_x[D3(b, i, j, k)] =
+                    ((vel * ((b->quick_x[Q2(b, i, j, 1)] * Tt[D3(b, i, j, k)]) +
+                             (b->quick_x[Q2(b, i, j, 2)] * Tt[D3(b, i + 1, j, k)]))) -
+                     (upos * (((b->curv_xp[Q2(b, i, j, 1)] * t1) + (b->curv_xp[Q2(b, i, j, 2)] * t0)) +
+                              (b->curv_xp[Q2(b, i, j, 3)] * ((tq[H3(b, i - 1, j, k)] * (1.0 - eastmsk)) + (t0 * eastmsk)))))) -
+                    (uneg * (((b->curv_xn[Q2(b, i, j, 1)] * ((tq[H3(b, i + 2, j, k)] * (1.0 - westmsk)) + (t1 * westmsk))) +
+                              (b->curv_xn[Q2(b, i, j, 2)] * t1)) +
+                             (b->curv_xn[Q2(b, i, j, 3)] * t0)));
+            }
+        if (limit_with_upwind) { /* OTA:2610-2635 */
+            for (int j = 1; j <= nj; j++)
+                for (int i = 0; i <= ni; i++)
+                    if (tmask_limit[D3(b, i, j, k)] == 1.0) {
+                        double vel = u[D3(b, i, j, k)];
+                        double upos = 0.5 * (vel + fabs(vel));
+                        double uneg = 0.5 * (vel - fabs(vel));
+                        flux_x[D3(b, i, j, k)] =
+                            ((b->dyte[D2(b, i, j)] * ((upos * Tm1[D3(b, i, j, k)]) + (uneg * Tm1[D3(b, i + 1, j, k)]))) *
+                             b->tmask[D3(b, i, j, k)]) *
+                            b->tmask[D3(b, i + 1, j, k)];
+                    }
+            for (int j = 0; j <= nj; j++)
+                for (int i = 1; i <= ni; i++)
+                    if (tmask_limit[D3(b, i, j, k)] == 1.0) {
+                        double vel = v[D3(b, i, j, k)];
+                        double upos = 0.5 * (vel + fabs(vel));
+                        double uneg = 0.5 * (vel - fabs(vel));
+                        flux_y[D3(b, i, j, k)] =
+                            ((b->dxtn[D2(b, i, j)] * ((upos * Tm1[D3(b, i, j, k)]) + (uneg * Tm1[D3(b, i, j + 1, k)]))) *
+                             b->tmask[D3(b, i, j, k)]) *
+                            b->tmask[D3(b, i, j + 1, k)];
+                    }
+        }
+    }
+}
+
+/* OTA:2640  mpp_update_domains(flux_x, flux_y, Dom_flux, gridtype=CGRID_NE) on a folded-north domain.
+ * Result-changing effect on the points the divergence reads: on the fold line j = nj_g the NORTH-position
+ * component of the eastern half is replaced by minus its mirror image,
+ *     flux_y(i, nj_g) := -flux_y(ni_g+1-i, nj_g)   for i >= middle = (isg+ieg)/2+1
+ * (MPPI/mpp_domains_define.inc:1617, 2535-2549: recv overlap isd=max(isd,middle), j=jeg, folded=.true. ->
+ *  180-degree rotation flips the sign of non-SCALAR_PAIR vectors, MPPI/mpp_do_updateV.h).  Halo-1 points
+ * of flux_x/flux_y also get refreshed from their owners, but the owners compute bit-identical values there
+ * (same inputs through consistent halos), so only the fold line changes results.                        */
+void orc_fold_fix_flux(const orc_layout *L, double *const *flux_x, double *const *flux_y, int nk)
+{
+    (void)flux_x;
+    if (!L->fold_north) return;
+    int middle = (1 + L->ni_g) / 2 + 1;
+    int by = L->py - 1;
+    int njl = L->jend[by] - L->jbeg[by] + 1;
+    for (int ig = middle; ig <= L->ni_g; ig++) {
+        int is = L->ni_g + 1 - ig;
+        int dx = find_div(L->ibeg, L->iend, L->px, ig), sx = find_div(L->ibeg, L->iend, L->px, is);
+        int dni = L->iend[dx] - L->ibeg[dx] + 1, sni = L->iend[sx] - L->ibeg[sx] + 1;
+        double *d = flux_y[dx + L->px * by];
+        const double *s = flux_y[sx + L->px * by];
+        int il = ig - L->ibeg[dx] + 1, isl = is - L->ibeg[sx] + 1;
+        for (int k = 0; k < nk; k++)
+            d[(size_t)il + (size_t)(dni + 2) * ((size_t)njl + (size_t)(njl + 2) * k)] =
+                -s[(size_t)isl + (size_t)(sni + 2) * ((size_t)njl + (size_t)(njl + 2) * k)];
+    }
+}
+
+/* OTA:2642-2649 (quicker) == OTA:2282-2287 (upwind): tmask*(fx(i)-fx(i-1)+fy(j)-fy(j-1))*datr, negated by caller */
+void orc_horz_div(const orc_block *b, const double *fx, const double *fy, double *wrk1_out)
+{
+    memset(wrk1_out, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * b->nk); /* OTA:1925-1931 */
+    for (int k = 1; k <= b->nk; k++)
+        for (int j = 1; j <= b->nj; j++)
+            for (int i = 1; i <= b->ni; i++) {
+                double r = (b->tmask[D3(b, i, j, k)] *
+                            (((fx[D3(b, i, j, k)] - fx[D3(b, i - 1, j, k)]) + fy[D3(b, i, j, k)]) - fy[D3(b, i, j - 1, k)])) *
+                           b->datr[D2(b, i, j)];
+                wrk1_out[D3(b, i, j, k)] = -r;
+            }
+}
+
+/* OTA:2981-3031 */
+void orc_vert_quicker(const orc_block *b, const double *Tm1, const double *Tt, const double *w,
+                      const double *tmask_limit, double *flux_z, double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *tmask = b->tmask;
+    double *ft1 = (double *)calloc((size_t)ni * nj, sizeof(double));
+    memset(wrk1_out, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk); /* OTA:2116-2122 */
+    for (int k = 1; k <= nk; k++) {
+        int km1 = imax(k - 1, 1), kp1 = imin(k + 1, nk), p2 = imin(k + 2, nk);
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t c = (size_t)(i - 1) + (size_t)ni * (j - 1);
+                double vel = w[W3(b, i, j, k)];
+                double upos = 0.5 * (vel + fabs(vel));
+                double uneg = 0.5 * (vel - fabs(vel));
+                double ft2;
+                if (tmask_limit[D3(b, i, j, k)] == 1.0) {
+                    ft2 = (((uneg * Tm1[D3(b, i, j, k)]) + (upos * Tm1[D3(b, i, j, kp1)])) * tmask[D3(b, i, j, k)]) *
+                          tmask[D3(b, i, j, kp1)];
+                } else {
+                    double mp2 = tmask[D3(b, i, j, p2)];
+                    int kp2 = (int)lround((mp2 * (double)p2) + ((1.0 - mp2) * (double)kp1)); /* nint() */
+                    double upmsk = tmask[D3(b, i, j, k)] * (1.0 - tmask[D3(b, i, j, km1)]);
+                    const double *qz = b->quick_z, *zp = b->curv_zp, *zn = b->curv_zn;
+                    ft2 = ((vel * ((qz[(k - 1)] * Tt[D3(b, i, j, k)]) + (qz[(k - 1) + nk] * Tt[D3(b, i, j, kp1)]))) -
+                           (uneg * (((zp[(k - 1)] * Tm1[D3(b, i, j, kp1)]) + (zp[(k - 1) + nk] * Tm1[D3(b, i, j, k)])) +
+                                    (zp[(k - 1) + 2 * nk] * Tm1[D3(b, i, j, km1)])))) -
+                          (upos * (((zn[(k - 1)] * Tm1[D3(b, i, j, kp2)]) + (zn[(k - 1) + nk] * Tm1[D3(b, i, j, kp1)])) +
+                                   (zn[(k - 1) + 2 * nk] *
+                                    ((Tm1[D3(b, i, j, k)] * (1.0 - upmsk)) + (Tm1[D3(b, i, j, kp1)] * upmsk)))));
+                }
+                if (flux_z) flux_z[D3(b, i, j, k)] = b->dat[D2(b, i, j)] * ft2;
+                wrk1_out[D3(b, i, j, k)] = -(tmask[D3(b, i, j, k)] * (ft1[c] - ft2));
+                ft1[c] = ft2;
+            }
+    }
+    free(ft1);
+}
+
+/* OTA:2238-2294 */
+void orc_horz_upwind(const orc_block *b, const double *T, const double *u, const double *v, double *flux_x,
+                     double *flux_y, double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *tmask = b->tmask;
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 1; j <= nj; j++)
+            for (int i = 0; i <= ni; i++) {
+                double velocity = 0.5 * u[D3(b, i, j, k)];
+                double upos = velocity + fabs(velocity);
+                double uneg = velocity - fabs(velocity);
+                flux_x[D3(b, i, j, k)] =
+                    ((b->dyte[D2(b, i, j)] * ((upos * T[D3(b, i, j, k)]) + (uneg * T[D3(b, i + 1, j, k)]))) *
+                     tmask[D3(b, i, j, k)]) *
+                    tmask[D3(b, i + 1, j, k)];
+            }
+        for (int j = 0; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                double velocity = 0.5 * v[D3(b, i, j, k)];
+                double upos = velocity + fabs(velocity);
+                double uneg = velocity - fabs(velocity);
+                flux_y[D3(b, i, j, k)] =
+                    ((b->dxtn[D2(b, i, j)] * ((upos * T[D3(b, i, j, k)]) + (uneg * T[D3(b, i, j + 1, k)]))) *
+                     tmask[D3(b, i, j, k)]) *
+                    tmask[D3(b, i, j + 1, k)];
+            }
+    }
+    orc_horz_div(b, flux_x, flux_y, wrk1_out);
+}
+
+/* OTA:2792-2824 */
+void orc_vert_upwind(const orc_block *b, const double *T, const double *w, double *flux_z, double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *tmask = b->tmask;
+    double *ft1 = (double *)calloc((size_t)ni * nj, sizeof(double));
+    memset(wrk1_out, 0, sizeof(double) * (size_t)NX1(b) * NY1(b) * nk);
+    for (int k = 1; k <= nk; k++) {
+        int kp1 = imin(k + 1, nk);
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t c = (size_t)(i - 1) + (size_t)ni * (j - 1);
+                double velocity = 0.5 * w[W3(b, i, j, k)];
+                double wpos = velocity + fabs(velocity);
+                double wneg = velocity - fabs(velocity);
+                double ft2 = (((wneg * T[D3(b, i, j, k)]) + (wpos * T[D3(b, i, j, kp1)])) * tmask[D3(b, i, j, k)]) *
+                             tmask[D3(b, i, j, kp1)];
+                if (flux_z) flux_z[D3(b, i, j, k)] = b->dat[D2(b, i, j)] * ft2;
+                wrk1_out[D3(b, i, j, k)] = -(tmask[D3(b, i, j, k)] * (ft1[c] - ft2));
+                ft1[c] = ft2;
+            }
+    }
+    free(ft1);
+}
+
+/* OTA:1990-1996 / 2162-2168 */
+void orc_accumulate(const orc_block *b, const double *wrk1, double *th)
+{
+    for (int k = 1; k <= b->nk; k++)
+        for (int j = 1; j <= b->nj; j++)
+            for (int i = 1; i <= b->ni; i++) th[D3(b, i, j, k)] = th[D3(b, i, j, k)] + wrk1[D3(b, i, j, k)];
+}
+
+/* ocean_tracer.F90:2341-2350 */
+void orc_tracer_update(const orc_block *b, double dtime, const double *rho_taum1, const double *rho_dztr_taup1,
+                       const double *T_taum1, const double *th, double *T_taup1)
+{
+    for (int k = 1; k <= b->nk; k++)
+        for (int j = 1; j <= b->nj; j++)
+            for (int i = 1; i <= b->ni; i++) {
+                size_t q = D3(b, i, j, k);
+                T_taup1[q] = ((rho_taum1[q] * T_taum1[q]) + (dtime * th[q])) * rho_dztr_taup1[q];
+            }
+}
+
+/* MPPI/mpp_chksum_int.h:20-38 + mpp_chksum.h:20-41: wrap-around sum of the int64 bit patterns */
+int64_t orc_chksum(const double *a, int ni, int nj, int nk, int halo, const double *mask)
+{
+    uint64_t s = 0;
+    size_t nx = (size_t)ni + 2 * halo, ny = (size_t)nj + 2 * halo;
+    for (int k = 0; k < nk; k++)
+        for (int j = 0; j < nj; j++)
+            for (int i = 0; i < ni; i++) {
+                size_t q = (size_t)(i + halo) + nx * ((size_t)(j + halo) + ny * k);
+                double v = mask ? a[q] * mask[q] : a[q];
+                uint64_t bits;
+                memcpy(&bits, &v, 8);
+                s += bits;
+            }
+    return (int64_t)s;
+}
+
+/* ocean_tracer_diag.F90:2405-2408, compute domain, conversion = 1 */
+double orc_total_tracer(const orc_block *b, const double *rho, const double *T)
+{
+    double tot = 0.0;
+    for (int j = 1; j <= b->nj; j++)
+        for (int i = 1; i <= b->ni; i++) {
+            double tk = 0.0;
+            for (int k = 1; k <= b->nk; k++)
+                tk = tk + (((b->tmask[D3(b, i, j, k)] * b->dat[D2(b, i, j)]) * rho[D3(b, i, j, k)]) * T[D3(b, i, j, k)]);
+            tot += tk;
+        }
+    return tot;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-block driver = timed CPU baseline. One OpenMP thread per block stands in for one MPI rank;
+ * orc_update_halo stands in for mpp_update_domains(XUPDATE / YUPDATE) (OTA:4213-4240, 4302-4343).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_sweby_all_multiblock(const orc_layout *L, const orc_block *blocks, int ntr, double dtime,
+                              const double *const *T, const double *const *u, const double *const *v,
+                              const double *const *w, const double *const *rho, double *const *tm,
+                              double *const *th, double *const *adv, int nthreads)
+{
+    int nb = L->px * L->py;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int b = 0; b < nb; b++)
+        orc_sweby_all_z(&blocks[b], ntr, dtime, T + (size_t)b * ntr, w[b], rho[b], tm + (size_t)b * ntr, NULL, NULL);
+
+    double **f = (double **)malloc(sizeof(double *) * nb);
+    for (int n = 0; n < ntr; n++) {
+        for (int b = 0; b < nb; b++) f[b] = tm[(size_t)b * ntr + n];
+        orc_update_halo(L, f, blocks[0].nk, 2, ORC_XUPDATE);
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int b = 0; b < nb; b++)
+        orc_sweby_all_x(&blocks[b], ntr, dtime, T + (size_t)b * ntr, u[b], rho[b], tm + (size_t)b * ntr, NULL, NULL);
+
+    for (int n = 0; n < ntr; n++) {
+        for (int b = 0; b < nb; b++) f[b] = tm[(size_t)b * ntr + n];
+        orc_update_halo(L, f, blocks[0].nk, 2, ORC_YUPDATE);
+    }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int b = 0; b < nb; b++)
+        orc_sweby_all_y(&blocks[b], ntr, dtime, T + (size_t)b * ntr, u[b], v[b], w[b], rho[b], tm + (size_t)b * ntr,
+                        th + (size_t)b * ntr, adv + (size_t)b * ntr, NULL, NULL);
+    free(f);
+}

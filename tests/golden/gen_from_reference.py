@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN FORTRAN TEXT.
+
+    python tests/golden/gen_from_reference.py [case ...]
+
+Runs only where /root/reference exists (the build container).  It reads the loop nests of
+    /root/reference/src/mom5/ocean_tracers/ocean_tracer_advect.F90
+at generation time (nothing is copied into this repo), translates them statement by statement with
+tests/golden/f90interp.py and executes them in IEEE binary64 on small synthetic single-domain cases from
+mom5_b200.synthetic.  Inputs and outputs are stored together in tests/golden/<case>.npz; the C oracle
+(oracle/mom5adv_oracle.c) must reproduce every output array bit for bit (tests/test_oracle_golden.py).
+
+Routines executed from the reference text (line ranges located by their `subroutine`/`function` headers):
+    mdfl_init (mask part) .......... tmask_mdfl
+    quicker_init (weights part) .... quick_*, curv_*, dxt_quick, tmask_quick
+    advect_tracer_sweby_all ........ th_tendency, T_prog%wrk1, all registered diagnostics
+    horz_advect_tracer ............. dispatcher arms upwind / quicker / mdfl_sweby / dst_linear
+    vert_advect_tracer ............. dispatcher arms upwind / quicker
+What is NOT reference text: the halo filler standing in for FMS mpp_update_domains (single domain: cyclic
+wrap, folded north edge, walls untouched; CGRID_NE fold fix) -- that restates
+src/shared/mpp/include/mpp_domains_define.inc:4865-4885,2535-2549 and is checked separately against FMS's own
+known-answer pattern (test_mpp_domains.F90:5628-5634, 3749-3766) in tests/test_halo_kat.py.
+"""
+from __future__ import annotations
+
+import os
+import re
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from f90interp import FArray, FList, Obj, S, nint, translate_block, translate_routine  # noqa: E402
+from mom5_b200.domain import XUPDATE, YUPDATE, Decomposition  # noqa: E402
+from mom5_b200.synthetic import make_case  # noqa: E402
+
+OTA = "/root/reference/src/mom5/ocean_tracers/ocean_tracer_advect.F90"
+OPARAM = "/root/reference/src/mom5/ocean_core/ocean_parameters.F90"
+
+GOLDEN_CASES = {
+    # name -> (synthetic case, overrides)
+    "g_tripolar": ("mini_tripolar", dict(ni=20, nj=14, nk=7, ntr=3)),
+    "g_walls": ("mini_walls", dict(ni=13, nj=11, nk=6, ntr=2)),
+    "g_torus": ("mini_torus", dict(ni=16, nj=12, nk=5, ntr=2)),
+    "g_walls_rough": ("mini_walls", dict(ni=18, nj=10, nk=8, ntr=2, cfl=0.9, seed=1234)),
+}
+
+
+def find_routine(src, kind, name):
+    first = next(n for n, l in enumerate(src, 1) if re.match(rf"\s*{kind}\s+{name}\b", l, flags=re.I))
+    last = next(n for n in range(first, len(src) + 1) if re.match(rf"\s*end\s+{kind}\s+{name}\b", src[n - 1], flags=re.I))
+    return first, last
+
+
+def find_line(src, pattern, start=1):
+    return next(n for n in range(start, len(src) + 1) if re.search(pattern, src[n - 1]))
+
+
+def to_farray(t, lows):
+    """torch/numpy (nk?, ny, nx) C-order -> FArray with Fortran lower bounds"""
+    a = np.array(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float64, copy=True)
+    return FArray(data=a, lo=list(lows))
+
+
+class Halo:
+    """Single-domain stand-in for mpp_update_domains on halo-h scalar fields + the CGRID_NE fold fix."""
+
+    def __init__(self, dec: Decomposition, isc, iec, jsc, jec):
+        self.dec, self.ni, self.nj = dec, iec - isc + 1, jec - jsc + 1
+
+    def scalar(self, f: FArray, flags):
+        # a section actual argument such as field(:,:,:) arrives rebased to lower bound 1: recover the true
+        # bounds from the shape (the domain's halo width), as the dummy argument's declaration would
+        ni, nj = self.ni, self.nj
+        hx, hy = (f.a.shape[-1] - ni) // 2, (f.a.shape[-2] - nj) // 2
+        ilo, ihi, jlo, jhi = 1 - hx, ni + hx, 1 - hy, nj + hy
+        src = f.a.copy()
+        for j in range(jlo, jhi + 1):
+            j_in = 1 <= j <= nj
+            for i in range(ilo, ihi + 1):
+                i_in = 1 <= i <= ni
+                if i_in and j_in:
+                    continue
+                want = (flags & XUPDATE) if (j_in and not i_in) else (flags & YUPDATE) if (i_in and not j_in) \
+                    else ((flags & XUPDATE) and (flags & YUPDATE))
+                if not want:
+                    continue
+                s = self.dec.map_source(i, j)
+                if s is None:
+                    continue  # solid wall: untouched
+                f.a[..., j - jlo, i - ilo] = src[..., s[1] - jlo, s[0] - ilo]
+
+    def cgrid_ne(self, fx: FArray, fy: FArray):
+        """mpp_update_domains(flux_x, flux_y, Dom_flux, gridtype=CGRID_NE), halo 1, folded north + cyclic x."""
+        ni, nj = self.ni, self.nj
+        ilo, jlo = 1 - (fx.a.shape[-1] - ni) // 2, 1 - (fx.a.shape[-2] - nj) // 2
+        sx, sy = fx.a.copy(), fy.a.copy()
+        # E/W halo columns (cyclic): plain copies for both components
+        if self.dec.cyclic_x:
+            for f, s in ((fx, sx), (fy, sy)):
+                f.a[..., 1 - jlo:nj + 1 - jlo, 0 - ilo] = s[..., 1 - jlo:nj + 1 - jlo, ni - ilo]
+                f.a[..., 1 - jlo:nj + 1 - jlo, ni + 1 - ilo] = s[..., 1 - jlo:nj + 1 - jlo, 1 - ilo]
+        if self.dec.tripolar:
+            middle = (1 + ni) // 2 + 1
+            for i in range(middle, ni + 1):  # fold line, NORTH-position component, eastern half
+                fy.a[..., nj - jlo, i - ilo] = -sy[..., nj - jlo, ni + 1 - i - ilo]
+        # (north halo row j=nj+1 of either component is never read by the divergence loop)
+
+
+def build_env(gen, b, src):
+    s = gen.s
+    ni, nj, nk, ntr = s.ni, s.nj, s.nk, len(b.T)
+    isc, iec, jsc, jec = 1, ni, 1, nj
+    isd, ied, jsd, jed = 0, ni + 1, 0, nj + 1
+    dec = s.decomposition(1, 1)
+    env = dict(FArray=FArray, S=S, nint=nint, min=min, max=max, abs=abs,
+               isc=isc, iec=iec, jsc=jsc, jec=jec, isd=isd, ied=ied, jsd=jsd, jed=jed, nk=nk,
+               num_prog_tracers=ntr, XUPDATE=XUPDATE, YUPDATE=YUPDATE, CGRID_NE=2, FATAL=2,
+               onesixth=1.0 / 6.0, have_obc=False, async_domain_update=False, limit_with_upwind=False,
+               advect_sweby_all=True, zero_tracer_advect_horz=False, zero_tracer_advect_vert=False,
+               compute_gyre_overturn_diagnose=False, module_is_initialized=True, index_temp=1, index_salt=2,
+               CLOCK_ROUTINE=0)
+    # ADVECT_* scheme ids straight from ocean_parameters.F90
+    for l in open(OPARAM):
+        m = re.match(r"\s*integer, parameter, public :: (ADVECT_\w+)\s*=\s*(\d+)", l)
+        if m:
+            env[m.group(1)] = int(m.group(2))
+    g = b.grid2d
+    Grd = Obj(tripolar=bool(s.tripolar), dzt=to_farray(b.dzt, [1]), tmask=to_farray(b.tmask, [isd, jsd, 1]),
+              **{k: to_farray(g[k], [isd, jsd]) for k in ("dat", "datr", "dxt", "dyt", "dxte", "dyte", "dxtn", "dytn")})
+    env["Grd"] = Grd
+    env["Adv_vel"] = Obj(uhrho_et=to_farray(b.uhrho_et, [isd, jsd, 1]), vhrho_nt=to_farray(b.vhrho_nt, [isd, jsd, 1]),
+                         wrho_bt=to_farray(b.wrho_bt, [isd, jsd, 0]))
+    taum1, tau, taup1 = 1, 2, 3
+    env["Time"] = Obj(taum1=taum1, tau=tau, taup1=taup1)
+    rho4 = np.stack([b.rho_dzt.numpy() * 0.97, b.rho_dzt.numpy(), b.rho_dzt.numpy() * 1.01])  # (3,nk,ny,nx): only tau is read
+    env["Thickness"] = Obj(rho_dzt=FArray(data=rho4.copy(), lo=[isd, jsd, 1, 1]))
+    env["Dens"] = Obj()
+    tracers = []
+    for n in range(ntr):
+        f4 = np.stack([b.T[n].numpy(), b.T_tau[n].numpy(), np.zeros_like(b.T[n].numpy())])
+        tracers.append(Obj(field=FArray(data=f4.copy(), lo=[isd, jsd, 1, 1]),
+                           th_tendency=to_farray(b.th_tendency[n], [isd, jsd, 1]),
+                           wrk1=FArray([(isd, ied), (jsd, jed), (1, nk)], fill=-777.0),
+                           tmask_limit=to_farray(b.tmask_limit[n], [isd, jsd, 1]),
+                           conversion=1.0, complete=(n == ntr - 1), name=f"tr{n + 1}",
+                           horz_advect_scheme=0, vert_advect_scheme=0))
+    env["T_prog"] = FList(tracers)
+    d1 = lambda: FArray([(isd, ied), (jsd, jed), (1, nk)])
+    h2 = lambda: FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2), (1, nk)])
+    for nm in ("flux_x", "flux_y", "flux_z", "wrk1", "advect_tendency", "neutral_temp_advect", "neutral_salt_advect"):
+        env[nm] = d1()
+    for nm in ("tmask_mdfl", "tracer_mdfl", "tmask_quick", "tracer_quick"):
+        env[nm] = h2()
+    env["tracer_mdfl_all"] = FList([Obj(field=h2()) for _ in range(ntr)])
+    env["dxt_quick"] = FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2)])
+    env["dyt_quick"] = FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2)])
+    for nm, c in (("quick_x", 2), ("quick_y", 2), ("curv_xp", 3), ("curv_xn", 3), ("curv_yp", 3), ("curv_yn", 3)):
+        env[nm] = FArray([(isd, ied), (jsd, jed), (1, c)])
+    for nm, c in (("quick_z", 2), ("curv_zp", 3), ("curv_zn", 3)):
+        env[nm] = FArray([(1, nk), (1, c)])
+    env["Dom_mdfl"] = env["Dom_quicker"] = env["Dom_flux"] = Obj(domain2d="halo")
+    env["Dom"] = Obj(maskmap=None, domain2d="halo")
+
+    halo = Halo(dec, isc, iec, jsc, jec)
+    diags = {}
+    DIAG_IDS = ["zflux_adv", "advection_z", "xflux_adv", "advection_x", "xflux_adv_int_z", "yflux_adv", "advection_y",
+                "yflux_adv_int_z", "sweby_advect", "horz_advect", "vert_advect", "tracer_advection", "psom_advect",
+                "tracer_advection_on_nrho", "tracer_adv_diss"]
+    OFF = {"psom_advect", "tracer_advection_on_nrho", "tracer_adv_diss"}
+    for q, nm in enumerate(DIAG_IDS):
+        env["id_" + nm] = (lambda n, q=q, nm=nm: -1 if nm in OFF else (q + 1) * 100 + n)
+
+    def diagnose(Time, Grd_, id_, data, *a, **k):
+        nm, n = DIAG_IDS[id_ // 100 - 1], id_ % 100
+        diags[f"{nm}.{n}"] = np.array(data.a, copy=True)
+
+    def update_domains(*args, flags=XUPDATE | YUPDATE, complete=None, gridtype=None, **kw):
+        fields = [a for a in args if isinstance(a, FArray)]
+        if gridtype is not None:
+            halo.cgrid_ne(fields[0], fields[1])
+        else:
+            for f in fields:
+                halo.scalar(f, flags)
+        return 1
+
+    def start_update(field, dom, flags=XUPDATE | YUPDATE, complete=None, **kw):
+        halo.scalar(field, flags)
+        return 1
+
+    def fatal(*a, **k):
+        raise RuntimeError("mpp_error: " + " ".join(str(x) for x in a))
+
+    noop = lambda *a, **k: 0
+    env.update(mpp_clock_begin=noop, mpp_clock_end=noop, mpp_clock_id=noop, set_ocean_domain=noop,
+               watermass_diag=noop, gyre_overturn_diagnose=noop, compute_adv_diss=noop,
+               store_ocean_obc_tracer_flux=noop, ocean_obc_zero_boundary=noop,
+               mpp_update_domains=update_domains, mpp_start_update_domains=start_update,
+               mpp_complete_update_domains=noop, diagnose_3d=diagnose, diagnose_2d=diagnose,
+               diagnose_3d_rho=noop, mpp_error=fatal)
+    # id_clock_* names are referenced as plain variables
+    for l in src:
+        for m in re.finditer(r"\b(id_clock_\w+)", l):
+            env.setdefault(m.group(1), 0)
+    return env, diags
+
+
+def run_case(name):
+    base, over = GOLDEN_CASES[name]
+    gen = make_case(base, **over)
+    b = gen.block(with_tau=True)
+    src = open(OTA).read().split("\n")
+    env, diags = build_env(gen, b, src)
+    s = gen.s
+    arrays = [k for k, v in env.items() if isinstance(v, FArray)]
+
+    def load_routine(kind, nm):
+        first, last = find_routine(src, kind, nm)
+        code, _ = translate_routine(src, first, last, array_names=arrays)
+        exec(compile(code, f"<OTA:{first}-{last} {nm}>", "exec"), env)
+        return first, last
+
+    cites = {}
+    for kind, nm in (("subroutine", "advect_tracer_sweby_all"), ("function", "advect_tracer_mdfl_sweby"),
+                     ("function", "horz_advect_tracer_upwind"), ("function", "vert_advect_tracer_upwind"),
+                     ("function", "horz_advect_tracer_quicker"), ("function", "vert_advect_tracer_quicker"),
+                     ("subroutine", "horz_advect_tracer"), ("subroutine", "vert_advect_tracer")):
+        cites[nm] = load_routine(kind, nm)
+
+    out = {}
+    # ---- mdfl_init: mask fill + halo update (tmask_mdfl = 0.0 ... mpp_update_domains) ----
+    f0, l0 = find_routine(src, "subroutine", "mdfl_init")
+    a = find_line(src, r"^\s*tmask_mdfl\s*=\s*0\.0", f0)
+    z = find_line(src, r"call mpp_update_domains\(tmask_mdfl", a)
+    code = translate_block(src, a, z, array_names=arrays)
+    code = "\n".join(l for l in code.split("\n") if not re.match(r"\s*(mass_mdfl|tracermass_mdfl)", l))
+    exec(compile(code, f"<OTA:{a}-{z} mdfl_init>", "exec"), env)
+    out["tmask_mdfl"] = env["tmask_mdfl"].a.copy()
+
+    T_prog = env["T_prog"]
+    ntr = len(T_prog.items)
+    th0 = [t.th_tendency.a.copy() for t in T_prog.items]
+
+    def reset():
+        for n, t in enumerate(T_prog.items):
+            t.th_tendency.a[...] = th0[n]
+            t.wrk1.a[...] = -777.0
+        diags.clear()
+
+    # ---- advect_tracer_sweby_all via the dispatcher (advect_sweby_all=.true., ntracer=1) ----
+    t0 = time.time()
+    env["advect_sweby_all"] = True
+    env["horz_advect_tracer"](env["Time"], env["Adv_vel"], env["Thickness"], env["Dens"], T_prog, T_prog(1), 1, s.dtime)
+    for n, t in enumerate(T_prog.items, 1):
+        out[f"sweby_all.th_tendency.{n}"] = t.th_tendency.a.copy()
+        out[f"sweby_all.wrk1.{n}"] = t.wrk1.a.copy()
+        out[f"sweby_all.tm.{n}"] = env["tracer_mdfl_all"](n).field.a.copy()
+    for k, v in diags.items():
+        out[f"sweby_all.diag.{k}"] = v
+    print(f"  sweby_all: {time.time() - t0:.1f}s, {len(diags)} diagnostics")
+
+    # ---- per-tracer dispatcher arms ----
+    env["advect_sweby_all"] = False
+    f0, l0 = find_routine(src, "subroutine", "quicker_init")
+    a = find_line(src, r"^\s*quick_x\s*=\s*0\.0", f0)
+    z = find_line(src, r"curv_zn\(k,3\)", a) + 1  # through the enddo of the k loop
+    code = translate_block(src, a, z, array_names=arrays)
+    exec(compile(code, f"<OTA:{a}-{z} quicker_init>", "exec"), env)
+    for nm in ("quick_x", "quick_y", "curv_xp", "curv_xn", "curv_yp", "curv_yn", "quick_z", "curv_zp", "curv_zn",
+               "dxt_quick", "dyt_quick", "tmask_quick"):
+        out[f"quicker_init.{nm}"] = env[nm].a.copy()
+
+    arms = [("upwind", "ADVECT_UPWIND", False), ("quicker", "ADVECT_QUICKER", False), ("quicker_lim", "ADVECT_QUICKER", True),
+            ("mdfl_sweby", "ADVECT_MDFL_SWEBY", False), ("dst_linear", "ADVECT_DST_LINEAR", False)]
+    for tag, scheme, lim in arms:
+        t0 = time.time()
+        reset()
+        env["limit_with_upwind"] = lim
+        n = 1 if tag != "quicker_lim" else min(2, ntr)
+        tr = T_prog(n)
+        tr.horz_advect_scheme = tr.vert_advect_scheme = env[scheme]
+        env["horz_advect_tracer"](env["Time"], env["Adv_vel"], env["Thickness"], env["Dens"], T_prog, tr, n, s.dtime)
+        out[f"{tag}.horz.wrk1"] = tr.wrk1.a.copy()
+        out[f"{tag}.horz.th_tendency"] = tr.th_tendency.a.copy()
+        out[f"{tag}.flux_x"] = env["flux_x"].a.copy()
+        out[f"{tag}.flux_y"] = env["flux_y"].a.copy()
+        env["vert_advect_tracer"](env["Time"], env["Adv_vel"], env["Dens"], env["Thickness"], T_prog, tr, n, s.dtime)
+        out[f"{tag}.vert.wrk1"] = tr.wrk1.a.copy()
+        out[f"{tag}.vert.th_tendency"] = tr.th_tendency.a.copy()
+        out[f"{tag}.flux_z"] = env["flux_z"].a.copy()
+        out[f"{tag}.tracer"] = np.array(n)
+        print(f"  {tag}: {time.time() - t0:.1f}s")
+
+    # ---- inputs ----
+    inp = dict(ni=s.ni, nj=s.nj, nk=s.nk, ntr=ntr, dtime=s.dtime, cyclic_x=s.cyclic_x, cyclic_y=s.cyclic_y,
+               tripolar=s.tripolar, dzt=b.dzt.numpy(), tmask=b.tmask.numpy(), rho_dzt=b.rho_dzt.numpy(),
+               uhrho_et=b.uhrho_et.numpy(), vhrho_nt=b.vhrho_nt.numpy(), wrho_bt=b.wrho_bt.numpy())
+    for k, v in b.grid2d.items():
+        inp["grid." + k] = v.numpy()
+    for n in range(ntr):
+        inp[f"T.{n + 1}"] = b.T[n].numpy()
+        inp[f"T_tau.{n + 1}"] = b.T_tau[n].numpy()
+        inp[f"th0.{n + 1}"] = th0[n]
+        inp[f"tmask_limit.{n + 1}"] = b.tmask_limit[n].numpy()
+    meta = "; ".join(f"{k}=OTA:{a}-{z}" for k, (a, z) in cites.items())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), __cites__=np.array(meta),
+                        **{"in." + k: v for k, v in inp.items()}, **{"out." + k: v for k, v in out.items()})
+    print(f"  wrote {name}.npz ({os.path.getsize(os.path.join(HERE, name + '.npz')) / 1e3:.0f} kB)")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(OTA):
+        sys.exit("the reference tree is not available here; golden vectors are committed under tests/golden/")
+    for nm in (sys.argv[1:] or list(GOLDEN_CASES)):
+        print(nm)
+        run_case(nm)

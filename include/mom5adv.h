@@ -1,0 +1,149 @@
+/*
+ * mom5adv.h -- C ABI of the B200-native MOM5 tracer-advection path (libmom5adv.so).
+ *
+ * The reference (MOM5, Fortran 90) has no FFI boundary on this path; the boundary is created at the
+ * call sites of ocean_tracer_advect_mod, cited per entry point below
+ * (OTA = src/mom5/ocean_tracers/ocean_tracer_advect.F90 in the reference tree).  The Fortran side binds
+ * these symbols through ISO_C_BINDING.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MOM5ADV_E* code on error; mom5adv_last_error()
+ *     returns a message.  Nothing aborts: the Fortran shim maps nonzero to mpp_error(FATAL, ...).
+ *   - all reals are IEEE binary64; arrays are Fortran column-major exactly as the reference dimensions them:
+ *       2-D  (isd:ied, jsd:jed)            3-D  (isd:ied, jsd:jed, nk)
+ *       wrho_bt (isd:ied, jsd:jed, 0:nk)   -- pass the address of the whole array (element (isd,jsd,0))
+ *     with isd = isc-1, ied = iec+1, jsd = jsc-1, jed = jec+1 (ocean_domains_nml halo = 1, ocean_domains.F90:77).
+ *   - "host" entry points take host pointers and are synchronous on return (H2D, kernels, D2H inside);
+ *     "_dev" entry points take DEVICE pointers of the same layout plus a cudaStream_t (as void*), enqueue
+ *     the work and return without synchronising.  The benchmarked path is the _dev one.
+ *   - one handle per rank/GPU; a handle is not thread safe.
+ *   - results are bit-identical to the reference arithmetic when the library is built with FMA
+ *     contraction disabled (the default build: nvcc --fmad=false).
+ */
+#ifndef MOM5ADV_H
+#define MOM5ADV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOM5ADV_VERSION 100
+
+/* error codes */
+#define MOM5ADV_OK 0
+#define MOM5ADV_EINVAL (-1)   /* bad argument */
+#define MOM5ADV_ECUDA (-2)    /* CUDA runtime error */
+#define MOM5ADV_ENCCL (-3)    /* NCCL error */
+#define MOM5ADV_ENOGPU (-4)   /* no CUDA device */
+#define MOM5ADV_EUNSUP (-5)   /* configuration the path does not cover (e.g. open boundaries) */
+
+/* scheme ids == ocean_parameters.F90:149-163 */
+#define MOM5ADV_ADVECT_UPWIND 1
+#define MOM5ADV_ADVECT_QUICKER 5
+#define MOM5ADV_ADVECT_MDFL_SWEBY 9
+#define MOM5ADV_ADVECT_DST_LINEAR 10
+
+typedef struct mom5adv_ctx *mom5adv_handle;
+typedef struct mom5adv_comm_s *mom5adv_comm; /* wraps an ncclComm_t; NULL = single rank */
+
+/* Filled by the caller (the ISO_C_BINDING shim, from Grd/Dom) once.  All pointers are HOST pointers and are
+ * only read during mom5adv_init.  Replaces the module state set up by ocean_tracer_advect_init
+ * (OTA:507-756), mdfl_init (OTA:1644-1691) and quicker_init (OTA:1442-1586).                            */
+typedef struct mom5adv_grid {
+    int isc, iec, jsc, jec;       /* compute domain, GLOBAL indices (ocean_domains.F90:311-318) */
+    int nk;
+    int ni_global, nj_global;
+    int layout_x, layout_y;       /* ocean_model_nml layout */
+    const int *x_extent;          /* [layout_x] compute extents per x-division, or NULL = mpp_compute_extent rule */
+    const int *y_extent;          /* [layout_y] */
+    int cyclic_x, cyclic_y, tripolar; /* ocean_types.F90:751-753 */
+    int have_obc;                 /* must be 0: open boundaries are not covered (-> MOM5ADV_EUNSUP) */
+    const double *dat, *datr, *dxt, *dyt, *dxte, *dyte, *dxtn, *dytn; /* (isd:ied, jsd:jed) */
+    const double *dzt;            /* (nk) Grd%dzt, for the quicker vertical weights */
+    const double *tmask;          /* (isd:ied, jsd:jed, nk) Grd%tmask */
+} mom5adv_grid;
+
+const char *mom5adv_last_error(void);
+int mom5adv_version(void);
+
+/* ---- communicator (only needed when layout_x*layout_y > 1) ------------------------------------------
+ * Replaces FMS mpp_update_domains for this path only.  Either let the library create its NCCL communicator
+ * (rank 0 calls mom5adv_comm_unique_id, the caller broadcasts the 128 bytes -- MPI_Bcast in the Fortran
+ * model, torch.distributed in bench.py -- then every rank calls mom5adv_comm_create), or wrap an existing
+ * ncclComm_t.  Rank r owns block (r % layout_x, r / layout_x), the FMS pelist order.                     */
+int mom5adv_comm_unique_id(char id_out[128]);
+int mom5adv_comm_create(const char id[128], int rank, int nranks, mom5adv_comm *out);
+int mom5adv_comm_from_nccl(void *nccl_comm, int rank, int nranks, mom5adv_comm *out);
+int mom5adv_comm_destroy(mom5adv_comm c);
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int mom5adv_init(const mom5adv_grid *grid, int ntracers_max, mom5adv_comm comm_or_null, mom5adv_handle *out);
+int mom5adv_finalize(mom5adv_handle h);
+
+/* ---- advect_tracer_sweby_all (OTA:4104-4511; called from horz_advect_tracer, OTA:2078-2080) -----------
+ * For n = 0..ntr-1:   adv_tendency[n] (= T_prog(n)%wrk1) := rho_dzt*(tm - T)/dtime*tmask on the compute
+ * domain, 0 on the halo ring;  th_tendency[n] += adv_tendency[n] on the compute domain.
+ * Optional per-tracer diagnostics (array of ntr pointers, or NULL; individual entries may be NULL):
+ *   flux_x (i=isc-1..iec), flux_y (j=jsc-1..jec), flux_z, and the per-direction tendencies adv_x/y/z
+ *   (the reference's shared wrk1 sent to diag ids *_advection_x/y/z); points outside the reference's loop
+ *   ranges are left untouched.                                                                           */
+int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime,
+                      const double *const *T_taum1, double *const *th_tendency, double *const *adv_tendency,
+                      const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
+                      const double *rho_dzt_tau,
+                      double *const *flux_x, double *const *flux_y, double *const *flux_z,
+                      double *const *adv_x, double *const *adv_y, double *const *adv_z);
+int mom5adv_sweby_all_dev(mom5adv_handle h, int ntr, double dtime,
+                          const double *const *T_taum1, double *const *th_tendency, double *const *adv_tendency,
+                          const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
+                          const double *rho_dzt_tau,
+                          double *const *flux_x, double *const *flux_y, double *const *flux_z,
+                          double *const *adv_x, double *const *adv_y, double *const *adv_z, void *stream);
+
+/* ---- horz_advect_tracer (OTA:1898-2083), one tracer, advect_sweby_all = .false. -----------------------
+ * scheme: UPWIND (OTA:2238-2294), QUICKER (OTA:2538-2653), MDFL_SWEBY / DST_LINEAR (OTA:3806-4066).
+ * wrk1_out (= Tracer%wrk1) := -scheme(...) on the compute domain, 0 on the halo ring;
+ * th_tendency += wrk1_out on the compute domain (OTA:1990-1996).  flux_x/flux_y/flux_z may be NULL.
+ * T_tau and tmask_limit are read by QUICKER only (tmask_limit only if limit_with_upwind != 0).           */
+int mom5adv_horz(mom5adv_handle h, int scheme, double dtime,
+                 const double *T_taum1, const double *T_tau, const double *tmask_limit, int limit_with_upwind,
+                 const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt, const double *rho_dzt_tau,
+                 double *th_tendency, double *wrk1_out, double *flux_x, double *flux_y, double *flux_z);
+int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime,
+                     const double *T_taum1, const double *T_tau, const double *tmask_limit, int limit_with_upwind,
+                     const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt, const double *rho_dzt_tau,
+                     double *th_tendency, double *wrk1_out, double *flux_x, double *flux_y, double *flux_z,
+                     void *stream);
+
+/* ---- vert_advect_tracer (OTA:2095-2226), one tracer ----------------------------------------------------
+ * scheme: UPWIND (OTA:2792-2824), QUICKER (OTA:2981-3031); MDFL_SWEBY / DST_LINEAR are three-dimensional:
+ * wrk1_out := 0 and th_tendency is unchanged (OTA:2147-2155).                                            */
+int mom5adv_vert(mom5adv_handle h, int scheme,
+                 const double *T_taum1, const double *T_tau, const double *tmask_limit,
+                 const double *wrho_bt, double *th_tendency, double *wrk1_out, double *flux_z);
+int mom5adv_vert_dev(mom5adv_handle h, int scheme,
+                     const double *T_taum1, const double *T_tau, const double *tmask_limit,
+                     const double *wrho_bt, double *th_tendency, double *wrk1_out, double *flux_z, void *stream);
+
+/* ---- metrics on device arrays ---------------------------------------------------------------------------
+ * mom5adv_chksum_dev: mpp_chksum of the compute domain (wrap-around sum of the int64 bit patterns,
+ * mpp_chksum_int.h:20-38), this rank's share; masked != 0 multiplies by tmask first
+ * (ocean_tracer_util.F90:562-566).  mom5adv_total_tracer_dev: sum tmask*dat*rho_dzt*T over the compute
+ * domain (ocean_tracer_diag.F90:2405-2408), this rank's share.                                           */
+int mom5adv_chksum_dev(mom5adv_handle h, const double *field3d, int masked, int64_t *out, void *stream);
+int mom5adv_total_tracer_dev(mom5adv_handle h, const double *rho_dzt, const double *T, double *out, void *stream);
+
+/* ---- introspection ------------------------------------------------------------------------------------- */
+/* device time of the last *_dev / host call per bucket, matching the reference's clocks
+ * (OTA:1678-1688): [0] z sweep (cuk)  [1] x sweep (cui)  [2] y sweep (cuj)  [3] halo/mpi  [4] total.
+ * Synchronises the handle's streams.                                                                     */
+int mom5adv_last_timing_ms(mom5adv_handle h, float ms[5]);
+/* number of kernels this library launched since init (all streams) */
+int64_t mom5adv_kernel_launches(mom5adv_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

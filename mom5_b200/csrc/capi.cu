@@ -1,0 +1,1024 @@
+// capi.cu -- extern "C" entry points of libmom5adv.so (see include/mom5adv.h) and the host-side driver:
+// domain bookkeeping, halo plans, launch configuration, stream/event handling.
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed on first use (see nccl_api below)
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/mom5adv.h"
+#include "halo.cuh"
+#include "horz_vert_kernels.cuh"
+#include "mom5adv_internal.cuh"
+#include "sweby_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *mom5adv_last_error(void) { return g_err; }
+extern "C" int mom5adv_version(void) { return MOM5ADV_VERSION; }
+
+// NCCL is bound at run time, not at link time: a host process that already carries an NCCL (PyTorch bundles its
+// own libnccl.so.2) must keep exactly that one -- a DT_NEEDED on the system copy would shadow it when this
+// library happens to be loaded first.  dlopen("libnccl.so.2") returns the already-loaded image if there is one.
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId;
+    decltype(&ncclCommInitRank) CommInitRank;
+    decltype(&ncclCommDestroy) CommDestroy;
+    decltype(&ncclGetErrorString) GetErrorString;
+    decltype(&ncclGroupStart) GroupStart;
+    decltype(&ncclGroupEnd) GroupEnd;
+    decltype(&ncclSend) Send;
+    decltype(&ncclRecv) Recv;
+};
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char *nm : {"libnccl.so.2", "libnccl.so"}) {
+            if ((api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+        }
+        if (api.lib) {
+#define NCCL_SYM(f) api.f = (decltype(api.f))dlsym(api.lib, "nccl" #f); if (!api.f) api.lib = nullptr
+            NCCL_SYM(GetUniqueId); NCCL_SYM(CommInitRank); NCCL_SYM(CommDestroy); NCCL_SYM(GetErrorString);
+            NCCL_SYM(GroupStart); NCCL_SYM(GroupEnd); NCCL_SYM(Send); NCCL_SYM(Recv);
+#undef NCCL_SYM
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+#define NCCL_NEED()                                                                                   \
+    NcclApi *N = nccl_api();                                                                          \
+    if (!N) { set_error("libnccl.so.2 could not be loaded: %s", dlerror()); return MOM5ADV_ENCCL; }
+
+#define NCCL_TRY(x)                                                                                   \
+    do {                                                                                              \
+        ncclResult_t r_ = (x);                                                                        \
+        if (r_ != ncclSuccess) {                                                                      \
+            set_error("NCCL error %s at %s:%d (%s)", N->GetErrorString(r_), __FILE__, __LINE__, #x);  \
+            return MOM5ADV_ENCCL;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct mom5adv_ctx {
+    Geom g;
+    int isc_g, jsc_g, ni_g, nj_g, px, py, ix, iy, rank;
+    int cyclic_x, cyclic_y, tripolar;
+    std::vector<int> ibeg, iend, jbeg, jend;
+    mom5adv_comm comm = nullptr;
+    int ntr_max = 0;
+    // static device data
+    double *dat = 0, *datr = 0, *dxte = 0, *dyte = 0, *dxtn = 0, *dytn = 0, *tmask = 0;
+    uint8_t *mask = 0;
+    QuickW qw{};                       // quicker weights (device)
+    std::vector<double *> tmA, tmB;    // h2 scratch per tracer
+    // halo machinery
+    HaloPlan plan[4];                  // indexed by flags (1 = X, 2 = Y, 3 = XY)
+    double *sendbuf = 0, *recvbuf = 0;
+    size_t bufcap = 0;
+    // host-pointer mode mirrors
+    std::vector<double *> hm;          // generic pool of data-domain device arrays
+    double *hm_w = 0;
+    cudaStream_t stream = 0;           // library-owned stream for the host-pointer entry points
+    cudaEvent_t ev[6];
+    bool ev_valid = false;
+    int64_t launches = 0;
+};
+
+#define LAUNCH(h, kern, grid, block, smem, st, ...)  \
+    do {                                             \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__); \
+        (h)->launches++;                             \
+    } while (0)
+
+static size_t n3(const mom5adv_ctx *h) { return (size_t)h->g.slab * h->g.nk; }
+static size_t nh2(const mom5adv_ctx *h) { return (size_t)h->g.tslab * h->g.nk; }
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers (mpp_compute_extent, MPPI/mpp_domains_define.inc:187-273)
+// ------------------------------------------------------------------------------------------------
+static int compute_extent(int isg, int ieg, int ndivs, std::vector<int> &ibegin, std::vector<int> &iend)
+{
+    ibegin.assign(ndivs, 0);
+    iend.assign(ndivs, 0);
+    const int npts = ieg - isg + 1;
+    const bool even_n = ndivs % 2 == 0, even_p = npts % 2 == 0;
+    const bool symmetrize = (even_n && even_p) || (!even_n && !even_p) || (!even_n && even_p && ndivs < npts / 2);
+    int is = isg, ie = 0, imax = ieg, ndmax = ndivs;
+    for (int ndiv = 0; ndiv < ndivs; ndiv++) {
+        if (ndiv < (ndivs - 1) / 2 + 1) {
+            ie = is + (int)std::ceil((double)(imax - is + 1) / (double)(ndmax - ndiv)) - 1;
+            const int ndmirror = (ndivs - 1) - ndiv;
+            if (ndmirror > ndiv && symmetrize) {
+                ibegin[ndmirror] = std::max(isg + ieg - ie, ie + 1);
+                iend[ndmirror] = std::max(isg + ieg - is, ie + 1);
+                imax = ibegin[ndmirror] - 1;
+                ndmax--;
+            }
+        } else if (symmetrize) {
+            is = ibegin[ndiv];
+            ie = iend[ndiv];
+        } else {
+            ie = is + (int)std::ceil((double)(imax - is + 1) / (double)(ndmax - ndiv)) - 1;
+        }
+        ibegin[ndiv] = is;
+        iend[ndiv] = ie;
+        if (ie < is) return 1;
+        if (ndiv == ndivs - 1 && iend[ndiv] != ieg) return 2;
+        is = ie + 1;
+    }
+    return 0;
+}
+
+static int find_div(const std::vector<int> &b, const std::vector<int> &e, int gidx)
+{
+    for (size_t d = 0; d < b.size(); d++)
+        if (gidx >= b[d] && gidx <= e[d]) return (int)d;
+    return -1;
+}
+
+// Build the message lists of one update (same algorithm as mom5_b200/domain.py:Decomposition.exchange_plan;
+// tests/test_plan.py checks the two against each other through mom5adv_debug_plan).
+struct DomInfo {
+    int ni_g, nj_g, px, py, cyclic_x, cyclic_y, tripolar;
+    const std::vector<int> *ibeg, *iend, *jbeg, *jend;
+};
+
+static void recv_strips(const DomInfo &D, int rank, int flags, int halo, std::vector<Msg> &recv, std::vector<Msg> &send_on_peer)
+{
+    const int bx = rank % D.px, by = rank / D.px;
+    const int i0g = (*D.ibeg)[bx], j0g = (*D.jbeg)[by];
+    const int ni = (*D.iend)[bx] - i0g + 1, nj = (*D.jend)[by] - j0g + 1;
+    struct R { int ia, ib, ja, jb; };
+    std::vector<R> regs;
+    if (flags & 1) { regs.push_back({1 - halo, 0, 1, nj}); regs.push_back({ni + 1, ni + halo, 1, nj}); }
+    if (flags & 2) { regs.push_back({1, ni, 1 - halo, 0}); regs.push_back({1, ni, nj + 1, nj + halo}); }
+    if ((flags & 1) && (flags & 2)) {
+        regs.push_back({1 - halo, 0, 1 - halo, 0});
+        regs.push_back({ni + 1, ni + halo, 1 - halo, 0});
+        regs.push_back({1 - halo, 0, nj + 1, nj + halo});
+        regs.push_back({ni + 1, ni + halo, nj + 1, nj + halo});
+    }
+    for (const R &r : regs) {
+        const bool beyond_n = (r.ja + j0g - 1) > D.nj_g;
+        const bool fold = D.tripolar && beyond_n;
+        const int nxr = r.ib - r.ia + 1, nyr = r.jb - r.ja + 1;
+        std::vector<int> sx(nxr), ox(nxr), sy(nyr), oy(nyr);
+        for (int p = 0; p < nxr; p++) {
+            int ig = r.ia + p + i0g - 1;
+            if (fold) ig = D.ni_g + 1 - ig;
+            bool ok = true;
+            if (ig < 1) { if (D.cyclic_x) ig += D.ni_g; else ok = false; }
+            else if (ig > D.ni_g) { if (D.cyclic_x) ig -= D.ni_g; else ok = false; }
+            if (ok && (ig < 1 || ig > D.ni_g)) ok = false;
+            sx[p] = ig;
+            ox[p] = ok ? find_div(*D.ibeg, *D.iend, ig) : -1;
+        }
+        for (int q = 0; q < nyr; q++) {
+            int jg = r.ja + q + j0g - 1;
+            bool ok = true;
+            if (jg > D.nj_g) {
+                if (D.tripolar) jg = 2 * D.nj_g + 1 - jg;
+                else if (D.cyclic_y) jg -= D.nj_g;
+                else ok = false;
+            } else if (jg < 1) {
+                if (D.cyclic_y) jg += D.nj_g; else ok = false;
+            }
+            if (ok && (jg < 1 || jg > D.nj_g)) ok = false;
+            sy[q] = jg;
+            oy[q] = ok ? find_div(*D.jbeg, *D.jend, jg) : -1;
+        }
+        // maximal runs of constant valid owner
+        auto runs = [](const std::vector<int> &o) {
+            std::vector<std::pair<int, int>> out;
+            int a = -1;
+            for (int q = 0; q < (int)o.size(); q++) {
+                if (o[q] >= 0 && a < 0) a = q;
+                if (a >= 0 && (q == (int)o.size() - 1 || o[q + 1] != o[a])) {
+                    out.push_back({a, q});
+                    a = -1;
+                }
+            }
+            return out;
+        };
+        for (auto rx : runs(ox))
+            for (auto ry : runs(oy)) {
+                const int peer = ox[rx.first] + D.px * oy[ry.first];
+                const int p_i0g = (*D.ibeg)[ox[rx.first]], p_j0g = (*D.jbeg)[oy[ry.first]];
+                int si_a = sx[rx.first] - p_i0g + 1, si_b = sx[rx.second] - p_i0g + 1;
+                int sj_a = sy[ry.first] - p_j0g + 1, sj_b = sy[ry.second] - p_j0g + 1;
+                Msg mr{peer, r.ia + rx.first, r.ia + rx.second, r.ja + ry.first, r.ja + ry.second, fold ? 1 : 0};
+                Msg ms{rank, std::min(si_a, si_b), std::max(si_a, si_b), std::min(sj_a, sj_b), std::max(sj_a, sj_b), fold ? 1 : 0};
+                recv.push_back(mr);
+                send_on_peer.push_back(ms);
+            }
+    }
+}
+
+static void build_plan(const DomInfo &D, int rank, int flags, int halo, HaloPlan &P)
+{
+    P.sends.clear();
+    P.recvs.clear();
+    for (int r = 0; r < D.px * D.py; r++) {
+        std::vector<Msg> rv, sd;
+        recv_strips(D, r, flags, halo, rv, sd);
+        for (size_t q = 0; q < rv.size(); q++) {
+            if (r == rank) P.recvs.push_back(rv[q]);
+            if (rv[q].peer == rank) {
+                Msg s = sd[q];
+                s.peer = r;
+                P.sends.push_back(s);
+            }
+        }
+    }
+}
+
+// debug / test hook: flat dump of a plan without any GPU. out: rows of 7 ints
+// (is_send, peer, i0, i1, j0, j1, flip); returns the number of rows (<= max_rows) or a negative error.
+extern "C" int mom5adv_debug_plan(int ni_g, int nj_g, int px, int py, int cyclic_x, int cyclic_y, int tripolar, int rank,
+                                  int flags, int halo, int *out, int max_rows)
+{
+    std::vector<int> ib, ie, jb, je;
+    if (compute_extent(1, ni_g, px, ib, ie) || compute_extent(1, nj_g, py, jb, je)) {
+        set_error("mom5adv_debug_plan: bad extents");
+        return MOM5ADV_EINVAL;
+    }
+    DomInfo D{ni_g, nj_g, px, py, cyclic_x, cyclic_y, tripolar, &ib, &ie, &jb, &je};
+    HaloPlan P;
+    build_plan(D, rank, flags, halo, P);
+    int n = 0;
+    for (int s = 1; s >= 0; s--)
+        for (const Msg &m : (s ? P.sends : P.recvs)) {
+            if (n >= max_rows) return n;
+            int *o = out + 7 * n++;
+            o[0] = s; o[1] = m.peer; o[2] = m.i0; o[3] = m.i1; o[4] = m.j0; o[5] = m.j1; o[6] = m.flip;
+        }
+    return n;
+}
+
+extern "C" int mom5adv_debug_extent(int isg, int ieg, int ndivs, int *ibegin, int *iend)
+{
+    std::vector<int> b, e;
+    int rc = compute_extent(isg, ieg, ndivs, b, e);
+    if (rc) return MOM5ADV_EINVAL;
+    for (int d = 0; d < ndivs; d++) { ibegin[d] = b[d]; iend[d] = e[d]; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// communicator
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_comm_unique_id(char id_out[128])
+{
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    NCCL_NEED();
+    NCCL_TRY(N->GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    return 0;
+}
+extern "C" int mom5adv_comm_create(const char id[128], int rank, int nranks, mom5adv_comm *out)
+{
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclComm_t c;
+    NCCL_NEED();
+    NCCL_TRY(N->CommInitRank(&c, nranks, uid, rank));
+    *out = new mom5adv_comm_s{(void *)c, rank, nranks, true};
+    return 0;
+}
+extern "C" int mom5adv_comm_from_nccl(void *nccl_comm, int rank, int nranks, mom5adv_comm *out)
+{
+    if (!nccl_comm) { set_error("mom5adv_comm_from_nccl: null communicator"); return MOM5ADV_EINVAL; }
+    *out = new mom5adv_comm_s{nccl_comm, rank, nranks, false};
+    return 0;
+}
+extern "C" int mom5adv_comm_destroy(mom5adv_comm c)
+{
+    if (!c) return 0;
+    if (c->owned && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)c->nccl);
+    delete c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo update of nf h2 fields
+// ------------------------------------------------------------------------------------------------
+static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags, cudaStream_t st)
+{
+    const HaloPlan &P = h->plan[flags & 3];
+    const int nk = h->g.nk;
+    for (int f0 = 0; f0 < nf; f0 += HALO_MAXF) {
+        const int nfc = std::min(HALO_MAXF, nf - f0);
+        // ---- local (self) strips ----
+        CopyArgs L{};
+        L.nf = nfc; L.nk = nk;
+        for (int n = 0; n < nfc; n++) L.f[n] = fields[f0 + n];
+        // match each self-recv with the self-send of the same ordinal
+        std::vector<const Msg *> rs, ss;
+        for (const Msg &m : P.recvs) if (m.peer == h->rank) rs.push_back(&m);
+        for (const Msg &m : P.sends) if (m.peer == h->rank) ss.push_back(&m);
+        if (rs.size() != ss.size()) { set_error("halo plan: self send/recv mismatch"); return MOM5ADV_EINVAL; }
+        auto flush_local = [&](CopyArgs &A) {
+            if (A.nmsg == 0) return;
+            A.total = A.start[A.nmsg];
+            const int nb = (int)std::min<long long>((A.total + 255) / 256, 148 * 16);
+            LAUNCH(h, k_halo<0>, nb, 256, 0, st, h->g, A);
+            A.nmsg = 0;
+        };
+        L.nmsg = 0; L.start[0] = 0;
+        for (size_t q = 0; q < rs.size(); q++) {
+            const Msg &r = *rs[q], &s = *ss[q];
+            CopyDesc d{};
+            d.si0 = s.i0; d.sj0 = s.j0; d.si1 = s.i1; d.sj1 = s.j1;
+            d.di0 = r.i0; d.dj0 = r.j0;
+            d.w = r.i1 - r.i0 + 1; d.h = r.j1 - r.j0 + 1; d.flip = r.flip;
+            L.d[L.nmsg] = d;
+            L.start[L.nmsg + 1] = L.start[L.nmsg] + (long long)d.w * d.h * nk * nfc;
+            if (++L.nmsg == HALO_MAXMSG) { flush_local(L); L.start[0] = 0; }
+        }
+        flush_local(L);
+
+        // ---- remote strips ----
+        std::vector<const Msg *> rr, sr;
+        for (const Msg &m : P.recvs) if (m.peer != h->rank) rr.push_back(&m);
+        for (const Msg &m : P.sends) if (m.peer != h->rank) sr.push_back(&m);
+        if (rr.empty() && sr.empty()) continue;
+        if (!h->comm) { set_error("halo update needs a communicator (layout %dx%d)", h->px, h->py); return MOM5ADV_EINVAL; }
+        // group by peer, keeping plan order within a peer
+        auto by_peer = [](std::vector<const Msg *> &v) {
+            std::stable_sort(v.begin(), v.end(), [](const Msg *a, const Msg *b) { return a->peer < b->peer; });
+        };
+        by_peer(rr); by_peer(sr);
+        if (rr.size() > HALO_MAXMSG || sr.size() > HALO_MAXMSG) { set_error("halo plan too large"); return MOM5ADV_EINVAL; }
+        CopyArgs S{}, R{};
+        S.nf = R.nf = nfc; S.nk = R.nk = nk;
+        for (int n = 0; n < nfc; n++) S.f[n] = R.f[n] = fields[f0 + n];
+        S.start[0] = R.start[0] = 0;
+        for (const Msg *m : sr) {
+            CopyDesc d{};
+            d.si0 = m->i0; d.sj0 = m->j0; d.si1 = m->i1; d.sj1 = m->j1;
+            d.w = m->i1 - m->i0 + 1; d.h = m->j1 - m->j0 + 1; d.flip = m->flip;
+            d.off = S.start[S.nmsg];
+            S.d[S.nmsg] = d;
+            S.start[S.nmsg + 1] = S.start[S.nmsg] + (long long)d.w * d.h * nk * nfc;
+            S.nmsg++;
+        }
+        for (const Msg *m : rr) {
+            CopyDesc d{};
+            d.di0 = m->i0; d.dj0 = m->j0;
+            d.w = m->i1 - m->i0 + 1; d.h = m->j1 - m->j0 + 1; d.flip = m->flip;
+            d.off = R.start[R.nmsg];
+            R.d[R.nmsg] = d;
+            R.start[R.nmsg + 1] = R.start[R.nmsg] + (long long)d.w * d.h * nk * nfc;
+            R.nmsg++;
+        }
+        S.total = S.start[S.nmsg];
+        R.total = R.start[R.nmsg];
+        const size_t need = (size_t)std::max(S.total, R.total);
+        if (need > h->bufcap) {
+            if (h->sendbuf) cudaFree(h->sendbuf);
+            if (h->recvbuf) cudaFree(h->recvbuf);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMalloc(&h->sendbuf, need * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->recvbuf, need * sizeof(double)));
+            h->bufcap = need;
+        }
+        S.buf = h->sendbuf;
+        R.buf = h->recvbuf;
+        if (S.total) {
+            const int nb = (int)std::min<long long>((S.total + 255) / 256, 148 * 16);
+            LAUNCH(h, k_halo<1>, nb, 256, 0, st, h->g, S);
+        }
+        ncclComm_t comm = (ncclComm_t)h->comm->nccl;
+        NCCL_NEED();
+        NCCL_TRY(N->GroupStart());
+        for (int m = 0; m < S.nmsg;) {   // one send per peer
+            int e = m;
+            while (e < S.nmsg && sr[e]->peer == sr[m]->peer) e++;
+            NCCL_TRY(N->Send(h->sendbuf + S.start[m], (size_t)(S.start[e] - S.start[m]), ncclDouble, sr[m]->peer, comm, st));
+            m = e;
+        }
+        for (int m = 0; m < R.nmsg;) {
+            int e = m;
+            while (e < R.nmsg && rr[e]->peer == rr[m]->peer) e++;
+            NCCL_TRY(N->Recv(h->recvbuf + R.start[m], (size_t)(R.start[e] - R.start[m]), ncclDouble, rr[m]->peer, comm, st));
+            m = e;
+        }
+        NCCL_TRY(N->GroupEnd());
+        if (R.total) {
+            const int nb = (int)std::min<long long>((R.total + 255) / 256, 148 * 16);
+            LAUNCH(h, k_halo<2>, nb, 256, 0, st, h->g, R);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// init / finalize
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int upload(T **dst, const T *src, size_t n)
+{
+    CUDA_TRY(cudaMalloc(dst, n * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int quicker_setup(mom5adv_ctx *h, const mom5adv_grid *G, cudaStream_t st);
+static int mirror(mom5adv_ctx *h, size_t idx, double **out);
+
+extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_comm comm, mom5adv_handle *out)
+{
+    if (!G || !out || ntracers_max < 1) { set_error("mom5adv_init: bad arguments"); return MOM5ADV_EINVAL; }
+    if (G->have_obc) { set_error("mom5adv_init: open boundaries (have_obc) are not covered by the GPU path"); return MOM5ADV_EUNSUP; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("mom5adv_init: no CUDA device"); return MOM5ADV_ENOGPU; }
+    if (G->tripolar && G->cyclic_y) { set_error("mom5adv_init: tripolar and cyclic_y are exclusive"); return MOM5ADV_EINVAL; }
+    if (G->tripolar && (G->ni_global % 2)) { set_error("mom5adv_init: tripolar fold needs an even ni_global"); return MOM5ADV_EINVAL; }
+    mom5adv_ctx *h = new mom5adv_ctx();
+    h->ntr_max = ntracers_max;
+    h->ni_g = G->ni_global; h->nj_g = G->nj_global; h->px = G->layout_x; h->py = G->layout_y;
+    h->cyclic_x = G->cyclic_x; h->cyclic_y = G->cyclic_y; h->tripolar = G->tripolar;
+    h->isc_g = G->isc; h->jsc_g = G->jsc;
+    auto from_extent = [](const int *ext, int n, int total, std::vector<int> &b, std::vector<int> &e) {
+        b.resize(n); e.resize(n);
+        int s = 1;
+        for (int d = 0; d < n; d++) { b[d] = s; e[d] = s + ext[d] - 1; s += ext[d]; }
+        return (s - 1 == total) ? 0 : 1;
+    };
+    int rc = G->x_extent ? from_extent(G->x_extent, h->px, h->ni_g, h->ibeg, h->iend) : compute_extent(1, h->ni_g, h->px, h->ibeg, h->iend);
+    rc |= G->y_extent ? from_extent(G->y_extent, h->py, h->nj_g, h->jbeg, h->jend) : compute_extent(1, h->nj_g, h->py, h->jbeg, h->jend);
+    if (rc) { set_error("mom5adv_init: invalid domain extents"); delete h; return MOM5ADV_EINVAL; }
+    h->ix = find_div(h->ibeg, h->iend, G->isc);
+    h->iy = find_div(h->jbeg, h->jend, G->jsc);
+    if (h->ix < 0 || h->iy < 0 || h->ibeg[h->ix] != G->isc || h->iend[h->ix] != G->iec || h->jbeg[h->iy] != G->jsc ||
+        h->jend[h->iy] != G->jec) {
+        set_error("mom5adv_init: compute domain (%d:%d,%d:%d) does not match layout %dx%d", G->isc, G->iec, G->jsc, G->jec, h->px, h->py);
+        delete h;
+        return MOM5ADV_EINVAL;
+    }
+    h->rank = h->ix + h->px * h->iy;
+    if (h->px * h->py > 1) {
+        if (!comm || comm->nranks != h->px * h->py || comm->rank != h->rank) {
+            set_error("mom5adv_init: layout %dx%d needs a communicator with %d ranks and rank == ix + px*iy", h->px, h->py, h->px * h->py);
+            delete h;
+            return MOM5ADV_EINVAL;
+        }
+        h->comm = comm;
+    }
+    Geom &g = h->g;
+    g.ni = G->iec - G->isc + 1; g.nj = G->jec - G->jsc + 1; g.nk = G->nk;
+    g.nxd = g.ni + 2; g.nyd = g.nj + 2; g.slab = (long long)g.nxd * g.nyd;
+    g.tpitch = ((g.ni + TOFF + 3) + 15) / 16 * 16; g.tslab = (long long)g.tpitch * (g.nj + 4);
+    g.mpitch = g.tpitch; g.mslab = g.tslab;
+    const size_t n2 = (size_t)g.slab;
+    if (upload(&h->dat, G->dat, n2) || upload(&h->datr, G->datr, n2) || upload(&h->dxte, G->dxte, n2) ||
+        upload(&h->dyte, G->dyte, n2) || upload(&h->dxtn, G->dxtn, n2) || upload(&h->dytn, G->dytn, n2) ||
+        upload(&h->tmask, G->tmask, n3(h))) { delete h; return MOM5ADV_ECUDA; }
+    CUDA_TRY(cudaMalloc(&h->mask, (size_t)g.mslab * g.nk));
+    CUDA_TRY(cudaMemset(h->mask, 0, (size_t)g.mslab * g.nk));
+    h->tmA.resize(ntracers_max); h->tmB.resize(ntracers_max);
+    for (int n = 0; n < ntracers_max; n++) {
+        CUDA_TRY(cudaMalloc(&h->tmA[n], nh2(h) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->tmB[n], nh2(h) * sizeof(double)));
+        CUDA_TRY(cudaMemset(h->tmA[n], 0, nh2(h) * sizeof(double)));   // wall halos stay 0 forever (OTA:1660-1666)
+        CUDA_TRY(cudaMemset(h->tmB[n], 0, nh2(h) * sizeof(double)));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int e = 0; e < 6; e++) CUDA_TRY(cudaEventCreate(&h->ev[e]));
+    DomInfo D{h->ni_g, h->nj_g, h->px, h->py, h->cyclic_x, h->cyclic_y, h->tripolar, &h->ibeg, &h->iend, &h->jbeg, &h->jend};
+    for (int f = 1; f <= 3; f++) build_plan(D, h->rank, f, 2, h->plan[f]);
+
+    // tmask_mdfl == tmask_quick: compute domain := Grd%tmask, full halo-2 update (OTA:1668-1675, 1478-1487), stored as u8
+    cudaStream_t st = h->stream;
+    dim3 gb((g.ni + 127) / 128, g.nj, g.nk);
+    LAUNCH(h, k_d1_to_h2, gb, 128, 0, st, g, h->tmask, h->tmA[0]);
+    double *f0[1] = {h->tmA[0]};
+    if ((rc = halo_update(h, f0, 1, 3, st))) { return rc; }
+    dim3 gm((g.ni + 4 + 127) / 128, g.nj + 4, g.nk);
+    LAUNCH(h, k_h2_to_mask, gm, 128, 0, st, g, h->tmA[0], h->mask);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemset(h->tmA[0], 0, nh2(h) * sizeof(double)));
+    if ((rc = quicker_setup(h, G, st))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    *out = h;
+    return 0;
+}
+
+extern "C" int mom5adv_finalize(mom5adv_handle h)
+{
+    if (!h) return 0;
+    cudaDeviceSynchronize();
+    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w})
+        if (p) cudaFree(p);
+    if (h->mask) cudaFree(h->mask);
+    for (double *p : h->tmA) cudaFree(p);
+    for (double *p : h->tmB) cudaFree(p);
+    for (double *p : h->hm) cudaFree(p);
+    free_quickw(h->qw);
+    for (int e = 0; e < 6; e++) cudaEventDestroy(h->ev[e]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sweby driver
+// ------------------------------------------------------------------------------------------------
+static int pick_kchunk(const Geom &g, int per_level_threads)
+{
+    // aim for >= ~4 resident waves of threads; each extra chunk costs one redundant face per column
+    const long long want = 148LL * 2048 * 2;
+    int nch = (int)std::min<long long>((want + per_level_threads - 1) / per_level_threads, std::max(1, g.nk / 8));
+    nch = std::max(nch, 1);
+    return (g.nk + nch - 1) / nch;
+}
+
+template <int NT, int VAR, bool DIAG>
+static void launch_group(mom5adv_ctx *h, int phase, const SwebyArgs<NT> &a, cudaStream_t st)
+{
+    const Geom &g = h->g;
+    SwebyArgs<NT> b = a;
+    if (phase == 0) {
+        b.kc = pick_kchunk(g, g.ni * g.nj);
+        dim3 grid((g.ni + ZBX - 1) / ZBX, (g.nj + ZBY - 1) / ZBY, (g.nk + b.kc - 1) / b.kc);
+        LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, dim3(ZBX, ZBY), 0, st, g, b);
+    } else if (phase == 1) {
+        b.kc = pick_kchunk(g, g.ni * g.nj);
+        dim3 grid((g.ni + 1 + XBX - 2) / (XBX - 1), (g.nj + XBY - 1) / XBY, (g.nk + b.kc - 1) / b.kc);
+        LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(XBX, XBY), 0, st, g, b);
+    } else {
+        const int nxt = (g.ni + YBX - 1) / YBX;
+        const long long per_chunk = (long long)nxt * YBX * g.nk;
+        int rows = 32;
+        while (rows > 8 && per_chunk * ((g.nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
+        b.kc = rows;
+        const int njc = (g.nj + rows - 1) / rows;
+        LAUNCH(h, (k_sweby_y<NT, VAR, DIAG>), (unsigned)(g.nk * nxt * njc), YBX, 0, st, g, b, nxt);
+    }
+}
+
+struct SwebyCall {
+    int ntr, var;
+    double dtime, sl;
+    const double *const *T;
+    double *const *th, *const *adv;
+    const double *u, *v, *w, *rho;
+    double *const *fx, *const *fy, *const *fz, *const *ax, *const *ay, *const *az;
+    int accumulate;
+};
+
+template <int NT>
+static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cudaStream_t st)
+{
+    SwebyArgs<NT> a{};
+    bool diag = false;
+    double *const *fl = phase == 0 ? c.fz : phase == 1 ? c.fx : c.fy;
+    double *const *da = phase == 0 ? c.az : phase == 1 ? c.ax : c.ay;
+    for (int n = 0; n < NT; n++) {
+        a.T[n] = c.T[n0 + n];
+        if (phase == 0) { a.tm_in[n] = h->tmA[n0 + n]; }
+        if (phase == 1) { a.tm_in[n] = h->tmA[n0 + n]; a.tm_out[n] = h->tmB[n0 + n]; }
+        if (phase == 2) { a.tm_in[n] = h->tmB[n0 + n]; a.th[n] = c.th ? c.th[n0 + n] : nullptr; a.adv[n] = c.adv[n0 + n]; }
+        a.flux[n] = fl ? fl[n0 + n] : nullptr;
+        a.dadv[n] = da ? da[n0 + n] : nullptr;
+        diag |= (a.flux[n] != nullptr) || (a.dadv[n] != nullptr);
+    }
+    a.u = c.u; a.v = c.v; a.w = c.w; a.rho = c.rho; a.mask = h->mask;
+    a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
+    a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;
+    if (c.var == VAR_ALL) {
+        if (diag) launch_group<NT, VAR_ALL, true>(h, phase, a, st);
+        else launch_group<NT, VAR_ALL, false>(h, phase, a, st);
+    } else {
+        if (diag) launch_group<NT, VAR_ONE, true>(h, phase, a, st);
+        else launch_group<NT, VAR_ONE, false>(h, phase, a, st);
+    }
+}
+
+static void run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, cudaStream_t st)
+{
+    for (int n0 = 0; n0 < c.ntr;) {
+        const int left = c.ntr - n0;
+        // groups of <= MAXNT tracers; prefer an even split (e.g. 10 = 4 + 3 + 3) over 4 + 4 + 2
+        const int ngroups = (left + MAXNT - 1) / MAXNT;
+        const int nt = (left + ngroups - 1) / ngroups;
+        switch (nt) {
+        case 1: run_phase<1>(h, c, n0, phase, st); break;
+        case 2: run_phase<2>(h, c, n0, phase, st); break;
+        case 3: run_phase<3>(h, c, n0, phase, st); break;
+        default: run_phase<4>(h, c, n0, phase, st); break;
+        }
+        n0 += nt;
+    }
+}
+
+static int zero_rings(mom5adv_ctx *h, double *const *arrs, int n, cudaStream_t st)
+{
+    for (int n0 = 0; n0 < n; n0 += MAXNT) {
+        RingArgs<MAXNT> r{};
+        for (int q = 0; q < MAXNT && n0 + q < n; q++) r.p[q] = arrs[n0 + q];
+        LAUNCH(h, k_zero_ring<MAXNT>, 64, 256, 0, st, h->g, r);
+    }
+    return 0;
+}
+
+static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
+{
+    if (c.ntr < 1 || c.ntr > h->ntr_max) { set_error("sweby: ntr=%d outside 1..%d", c.ntr, h->ntr_max); return MOM5ADV_EINVAL; }
+    int rc;
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    zero_rings(h, c.adv, c.ntr, st);
+    run_phase_all(h, c, 0, st);
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    run_phase_all(h, c, 1, st);
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    run_phase_all(h, c, 2, st);
+    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    h->ev_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mom5adv_sweby_all_dev(mom5adv_handle h, int ntr, double dtime, const double *const *T, double *const *th,
+                                     double *const *adv, const double *u, const double *v, const double *w, const double *rho,
+                                     double *const *fx, double *const *fy, double *const *fz, double *const *ax,
+                                     double *const *ay, double *const *az, void *stream)
+{
+    if (!h || !T || !th || !adv || !u || !v || !w || !rho) { set_error("mom5adv_sweby_all_dev: null argument"); return MOM5ADV_EINVAL; }
+    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, T, th, adv, u, v, w, rho, fx, fy, fz, ax, ay, az, 1};
+    return sweby_dev(h, c, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer mode: device mirrors + H2D / D2H around the _dev path
+// ------------------------------------------------------------------------------------------------
+static int mirror(mom5adv_ctx *h, size_t idx, double **out)
+{
+    while (h->hm.size() <= idx) {
+        double *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, n3(h) * sizeof(double)));
+        h->hm.push_back(p);
+    }
+    *out = h->hm[idx];
+    return 0;
+}
+static int mirror_w(mom5adv_ctx *h, double **out)
+{
+    if (!h->hm_w) CUDA_TRY(cudaMalloc(&h->hm_w, ((size_t)h->g.slab * (h->g.nk + 1)) * sizeof(double)));
+    *out = h->hm_w;
+    return 0;
+}
+#define H2D(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyDeviceToHost, st))
+
+extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const double *const *T, double *const *th,
+                                 double *const *adv, const double *u, const double *v, const double *w, const double *rho,
+                                 double *const *fx, double *const *fy, double *const *fz, double *const *ax, double *const *ay,
+                                 double *const *az)
+{
+    if (!h || !T || !th || !u || !v || !w || !rho) { set_error("mom5adv_sweby_all: null argument"); return MOM5ADV_EINVAL; }
+    if (ntr < 1 || ntr > h->ntr_max) { set_error("mom5adv_sweby_all: ntr=%d outside 1..%d", ntr, h->ntr_max); return MOM5ADV_EINVAL; }
+    cudaStream_t st = h->stream;
+    const size_t N = n3(h);
+    int rc;
+    size_t slot = 0;
+    double *du, *dv, *dw, *dr;
+    if ((rc = mirror(h, slot++, &du)) || (rc = mirror(h, slot++, &dv)) || (rc = mirror(h, slot++, &dr)) || (rc = mirror_w(h, &dw))) return rc;
+    std::vector<double *> dT(ntr), dth(ntr), dadv(ntr);
+    std::vector<const double *> cT(ntr);
+    for (int n = 0; n < ntr; n++) {
+        if ((rc = mirror(h, slot++, &dT[n])) || (rc = mirror(h, slot++, &dth[n])) || (rc = mirror(h, slot++, &dadv[n]))) return rc;
+        cT[n] = dT[n];
+    }
+    // optional diagnostics share per-kind mirrors
+    double *const *hd[6] = {fx, fy, fz, ax, ay, az};
+    std::vector<std::vector<double *>> dd(6);
+    for (int q = 0; q < 6; q++)
+        if (hd[q]) {
+            dd[q].assign(ntr, nullptr);
+            for (int n = 0; n < ntr; n++)
+                if (hd[q][n]) {
+                    if ((rc = mirror(h, slot++, &dd[q][n]))) return rc;
+                    H2D(dd[q][n], hd[q][n], N);   // points outside the loop ranges keep the caller's values
+                }
+        }
+    H2D(du, u, N); H2D(dv, v, N); H2D(dr, rho, N);
+    H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1));
+    for (int n = 0; n < ntr; n++) { H2D(dT[n], T[n], N); H2D(dth[n], th[n], N); }
+    auto arr = [&](int q) -> double *const * { return hd[q] ? dd[q].data() : nullptr; };
+    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, cT.data(), dth.data(), dadv.data(), du, dv, dw, dr, arr(0), arr(1), arr(2), arr(3), arr(4), arr(5), 1};
+    if ((rc = sweby_dev(h, c, st))) return rc;
+    for (int n = 0; n < ntr; n++) {
+        D2H(th[n], dth[n], N);
+        if (adv && adv[n]) D2H(adv[n], dadv[n], N);
+        for (int q = 0; q < 6; q++)
+            if (hd[q] && hd[q][n]) D2H(hd[q][n], dd[q][n], N);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// horz_advect_tracer / vert_advect_tracer (one tracer)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, const double *Tm1, const double *Tt,
+                                const double *tlimit, int limit_with_upwind, const double *u, const double *v, const double *w,
+                                const double *rho, double *th, double *wrk1, double *fx, double *fy, double *fz, void *stream)
+{
+    if (!h || !Tm1 || !u || !v || !th || !wrk1) { set_error("mom5adv_horz_dev: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom &g = h->g;
+    switch (scheme) {
+    case MOM5ADV_ADVECT_MDFL_SWEBY:
+    case MOM5ADV_ADVECT_DST_LINEAR: {
+        if (!w || !rho) { set_error("mom5adv_horz_dev: sweby needs wrho_bt and rho_dzt"); return MOM5ADV_EINVAL; }
+        // flux_x = flux_y = 0 (OTA:3837-3838)
+        if (fx) CUDA_TRY(cudaMemsetAsync(fx, 0, n3(h) * sizeof(double), st));
+        if (fy) CUDA_TRY(cudaMemsetAsync(fy, 0, n3(h) * sizeof(double), st));
+        const double *Ts[1] = {Tm1};
+        double *ths[1] = {th}, *advs[1] = {wrk1}, *fxs[1] = {fx}, *fys[1] = {fy}, *fzs[1] = {fz};
+        SwebyCall c{1, VAR_ONE, dtime, scheme == MOM5ADV_ADVECT_MDFL_SWEBY ? 1.0 : 0.0, Ts, ths, advs, u, v, w, rho,
+                    fx ? fxs : nullptr, fy ? fys : nullptr, fz ? fzs : nullptr, nullptr, nullptr, nullptr, 1};
+        return sweby_dev(h, c, st);
+    }
+    case MOM5ADV_ADVECT_UPWIND: {
+        double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
+        int rc;
+        if (!tfx && (rc = mirror(h, 0, &tfx))) return rc;
+        if (!tfy && (rc = mirror(h, 1, &tfy))) return rc;
+        return horz_upwind_dev(h->g, h->tmask, h->dyte, h->dxtn, h->datr, Tm1, u, v, th, wrk1, tfx, tfy, st, &h->launches);
+    }
+    case MOM5ADV_ADVECT_QUICKER: {
+        if (!Tt) { set_error("mom5adv_horz_dev: quicker needs T_tau"); return MOM5ADV_EINVAL; }
+        if (limit_with_upwind && !tlimit) { set_error("mom5adv_horz_dev: limit_with_upwind needs tmask_limit"); return MOM5ADV_EINVAL; }
+        // tracer_quick = 0; compute domain := T(taum1); full halo-2 update (OTA:2558-2566).  Wall halos of the
+        // scratch are never written and stay 0.
+        dim3 gb((g.ni + 127) / 128, g.nj, g.nk);
+        LAUNCH(h, k_d1_to_h2, gb, 128, 0, st, g, Tm1, h->tmA[0]);
+        double *f0[1] = {h->tmA[0]};
+        int rc = halo_update(h, f0, 1, 3, st);
+        if (rc) return rc;
+        double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
+        if (!tfx && (rc = mirror(h, 0, &tfx))) return rc;
+        if (!tfy && (rc = mirror(h, 1, &tfy))) return rc;
+        rc = horz_quicker_dev(h->g, h->qw, h->tmask, h->mask, h->dyte, h->dxtn, h->datr, Tm1, Tt, h->tmA[0], tlimit,
+                              limit_with_upwind, u, v, th, wrk1, tfx, tfy, h->tripolar, h->ni_g, h->isc_g,
+                              h->jsc_g + g.nj - 1 == h->nj_g, st, &h->launches);
+        if (rc == -100) { set_error("quicker on a tripolar grid split in x needs the fold-line exchange (not implemented): use layout_x = 1"); return MOM5ADV_EUNSUP; }
+        return rc;
+    }
+    default:
+        set_error("mom5adv_horz_dev: chose invalid horz advection scheme %d", scheme);   // OTA:1983-1985
+        return MOM5ADV_EINVAL;
+    }
+}
+
+extern "C" int mom5adv_vert_dev(mom5adv_handle h, int scheme, const double *Tm1, const double *Tt, const double *tlimit,
+                                const double *w, double *th, double *wrk1, double *fz, void *stream)
+{
+    if (!h || !wrk1 || !th) { set_error("mom5adv_vert_dev: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (scheme) {
+    case MOM5ADV_ADVECT_MDFL_SWEBY:
+    case MOM5ADV_ADVECT_DST_LINEAR:   // three-dimensional schemes: wrk1 = 0, th unchanged (OTA:2116-2122, 2147-2155)
+        CUDA_TRY(cudaMemsetAsync(wrk1, 0, n3(h) * sizeof(double), st));
+        return 0;
+    case MOM5ADV_ADVECT_UPWIND:
+        if (!Tm1 || !w) { set_error("mom5adv_vert_dev: null argument"); return MOM5ADV_EINVAL; }
+        return vert_dev(h->g, h->qw, h->tmask, h->dat, Tm1, Tm1, nullptr, w, th, wrk1, fz, 0, st, &h->launches);
+    case MOM5ADV_ADVECT_QUICKER:
+        if (!Tm1 || !Tt || !tlimit || !w) { set_error("mom5adv_vert_dev: quicker needs T_taum1, T_tau, tmask_limit, wrho_bt"); return MOM5ADV_EINVAL; }
+        return vert_dev(h->g, h->qw, h->tmask, h->dat, Tm1, Tt, tlimit, w, th, wrk1, fz, 1, st, &h->launches);
+    default:
+        set_error("mom5adv_vert_dev: invalid advection scheme chosen %d", scheme);   // OTA:2157-2159
+        return MOM5ADV_EINVAL;
+    }
+}
+
+extern "C" int mom5adv_horz(mom5adv_handle h, int scheme, double dtime, const double *Tm1, const double *Tt, const double *tlimit,
+                            int limit_with_upwind, const double *u, const double *v, const double *w, const double *rho,
+                            double *th, double *wrk1, double *fx, double *fy, double *fz)
+{
+    if (!h || !Tm1 || !u || !v || !th || !wrk1) { set_error("mom5adv_horz: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = h->stream;
+    const size_t N = n3(h);
+    int rc;
+    // slots 0,1 are reserved as flux scratch by the quicker path
+    size_t slot = 2;
+    double *dTm1, *dTt = 0, *dtl = 0, *du, *dv, *dw = 0, *dr = 0, *dth, *dwrk, *dfx = 0, *dfy = 0, *dfz = 0;
+    if ((rc = mirror(h, slot++, &dTm1)) || (rc = mirror(h, slot++, &du)) || (rc = mirror(h, slot++, &dv)) ||
+        (rc = mirror(h, slot++, &dth)) || (rc = mirror(h, slot++, &dwrk))) return rc;
+    H2D(dTm1, Tm1, N); H2D(du, u, N); H2D(dv, v, N); H2D(dth, th, N);
+    if (Tt) { if ((rc = mirror(h, slot++, &dTt))) return rc; H2D(dTt, Tt, N); }
+    if (tlimit) { if ((rc = mirror(h, slot++, &dtl))) return rc; H2D(dtl, tlimit, N); }
+    if (rho) { if ((rc = mirror(h, slot++, &dr))) return rc; H2D(dr, rho, N); }
+    if (w) { if ((rc = mirror_w(h, &dw))) return rc; H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1)); }
+    if (fx) { if ((rc = mirror(h, slot++, &dfx))) return rc; H2D(dfx, fx, N); }
+    if (fy) { if ((rc = mirror(h, slot++, &dfy))) return rc; H2D(dfy, fy, N); }
+    if (fz) { if ((rc = mirror(h, slot++, &dfz))) return rc; H2D(dfz, fz, N); }
+    if ((rc = mom5adv_horz_dev(h, scheme, dtime, dTm1, dTt, dtl, limit_with_upwind, du, dv, dw, dr, dth, dwrk, dfx, dfy, dfz, st))) return rc;
+    D2H(th, dth, N); D2H(wrk1, dwrk, N);
+    if (fx) D2H(fx, dfx, N);
+    if (fy) D2H(fy, dfy, N);
+    if (fz) D2H(fz, dfz, N);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int mom5adv_vert(mom5adv_handle h, int scheme, const double *Tm1, const double *Tt, const double *tlimit, const double *w,
+                            double *th, double *wrk1, double *fz)
+{
+    if (!h || !th || !wrk1) { set_error("mom5adv_vert: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = h->stream;
+    const size_t N = n3(h);
+    int rc;
+    size_t slot = 2;
+    double *dTm1 = 0, *dTt = 0, *dtl = 0, *dw = 0, *dth, *dwrk, *dfz = 0;
+    if ((rc = mirror(h, slot++, &dth)) || (rc = mirror(h, slot++, &dwrk))) return rc;
+    H2D(dth, th, N);
+    if (Tm1) { if ((rc = mirror(h, slot++, &dTm1))) return rc; H2D(dTm1, Tm1, N); }
+    if (Tt) { if ((rc = mirror(h, slot++, &dTt))) return rc; H2D(dTt, Tt, N); }
+    if (tlimit) { if ((rc = mirror(h, slot++, &dtl))) return rc; H2D(dtl, tlimit, N); }
+    if (w) { if ((rc = mirror_w(h, &dw))) return rc; H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1)); }
+    if (fz) { if ((rc = mirror(h, slot++, &dfz))) return rc; H2D(dfz, fz, N); }
+    if ((rc = mom5adv_vert_dev(h, scheme, dTm1, dTt, dtl, dw, dth, dwrk, dfz, st))) return rc;
+    D2H(th, dth, N); D2H(wrk1, dwrk, N);
+    if (fz) D2H(fz, dfz, N);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// metrics
+// ------------------------------------------------------------------------------------------------
+__global__ void k_chksum(const Geom g, const double *__restrict__ f, const double *__restrict__ tmask, unsigned long long *out)
+{
+    unsigned long long s = 0;
+    const long long tot = (long long)g.ni * g.nj * g.nk;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % g.ni) + 1;
+        const int j = (int)((e / g.ni) % g.nj) + 1;
+        const int k = (int)(e / ((long long)g.ni * g.nj)) + 1;
+        double v = f[d3(g, i, j, k)];
+        if (tmask) v = v * tmask[d3(g, i, j, k)];
+        s += (unsigned long long)__double_as_longlong(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// per-column partial sums in the reference's order, then an (order-free up to round-off) column reduction
+__global__ void k_total_tracer(const Geom g, const double *__restrict__ tmask, const double *__restrict__ dat,
+                               const double *__restrict__ rho, const double *__restrict__ T, double *out)
+{
+    double s = 0.0;
+    const long long tot = (long long)g.ni * g.nj;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % g.ni) + 1, j = (int)(e / g.ni) + 1;
+        double tk = 0.0;
+        for (int k = 1; k <= g.nk; k++)
+            tk = tk + (((tmask[d3(g, i, j, k)] * dat[d2(g, i, j)]) * rho[d3(g, i, j, k)]) * T[d3(g, i, j, k)]);
+        s += tk;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+extern "C" int mom5adv_chksum_dev(mom5adv_handle h, const double *f, int masked, int64_t *out, void *stream)
+{
+    if (!h || !f || !out) { set_error("mom5adv_chksum_dev: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 8, st));
+    LAUNCH(h, k_chksum, 148 * 8, 256, 0, st, h->g, f, masked ? h->tmask : nullptr, d);
+    CUDA_TRY(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int mom5adv_total_tracer_dev(mom5adv_handle h, const double *rho, const double *T, double *out, void *stream)
+{
+    if (!h || !rho || !T || !out) { set_error("mom5adv_total_tracer_dev: null argument"); return MOM5ADV_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *d;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 8, st));
+    LAUNCH(h, k_total_tracer, 148 * 4, 256, 0, st, h->g, h->tmask, h->dat, rho, T, d);
+    CUDA_TRY(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int mom5adv_last_timing_ms(mom5adv_handle h, float ms[5])
+{
+    if (!h || !ms) { set_error("mom5adv_last_timing_ms: null argument"); return MOM5ADV_EINVAL; }
+    for (int q = 0; q < 5; q++) ms[q] = 0.f;
+    if (!h->ev_valid) return 0;
+    CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+    float hx = 0, hy = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms[0], h->ev[0], h->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&hx, h->ev[1], h->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[1], h->ev[2], h->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&hy, h->ev[3], h->ev[4]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[2], h->ev[4], h->ev[5]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[4], h->ev[0], h->ev[5]));
+    ms[3] = hx + hy;
+    return 0;
+}
+
+extern "C" int64_t mom5adv_kernel_launches(mom5adv_handle h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// quicker_init on device (OTA:1442-1586)
+// ------------------------------------------------------------------------------------------------
+static int quicker_setup(mom5adv_ctx *h, const mom5adv_grid *G, cudaStream_t st)
+{
+    // dxt_quick / dyt_quick: compute domain := dxt, dyt; edge replication (OTA:1490-1509); full halo-2 update where an
+    // image exists (OTA:1510-1511).  Done on the host for the replication part (2-D, once), on the device for the update.
+    const Geom &g = h->g;
+    const int nx2 = g.ni + 4, ny2 = g.nj + 4;
+    if (!G->dxt || !G->dyt || !G->dzt) { set_error("mom5adv_init: dxt, dyt, dzt are required"); return MOM5ADV_EINVAL; }
+    std::vector<double> dx((size_t)nx2 * ny2, 0.0), dy((size_t)nx2 * ny2, 0.0);
+    auto H = [&](int i, int j) { return (size_t)(i + 1) + (size_t)nx2 * (j + 1); };
+    auto D = [&](int i, int j) { return (size_t)i + (size_t)g.nxd * j; };
+    for (int j = 1; j <= g.nj; j++)
+        for (int i = 1; i <= g.ni; i++) { dx[H(i, j)] = G->dxt[D(i, j)]; dy[H(i, j)] = G->dyt[D(i, j)]; }
+    for (int i = -1; i <= 0; i++) {
+        for (int j = 1; j <= g.nj; j++) dx[H(i, j)] = dx[H(1, j)];
+        for (int j = -1; j <= g.nj + 2; j++) dy[H(i, j)] = dy[H(1, j)];
+    }
+    for (int i = g.ni + 1; i <= g.ni + 2; i++) {
+        for (int j = 1; j <= g.nj; j++) dx[H(i, j)] = dx[H(g.ni, j)];
+        for (int j = -1; j <= g.nj + 2; j++) dy[H(i, j)] = dy[H(g.ni, j)];
+    }
+    for (int j = -1; j <= 0; j++)
+        for (int i = -1; i <= g.ni + 2; i++) { dx[H(i, j)] = dx[H(i, 1)]; dy[H(i, j)] = dy[H(i, 1)]; }
+    for (int j = g.nj + 1; j <= g.nj + 2; j++)
+        for (int i = -1; i <= g.ni + 2; i++) { dx[H(i, j)] = dx[H(i, g.nj)]; dy[H(i, j)] = dy[H(i, g.nj)]; }
+    // stage into one-level h2 fields on the device, update, read back
+    Geom g1 = g;
+    g1.nk = 1;
+    std::vector<double> sx((size_t)g.tslab, 0.0), sy((size_t)g.tslab, 0.0);
+    for (int j = -1; j <= g.nj + 2; j++)
+        for (int i = -1; i <= g.ni + 2; i++) { sx[t3(g1, i, j, 1)] = dx[H(i, j)]; sy[t3(g1, i, j, 1)] = dy[H(i, j)]; }
+    double *dsx = h->tmA[0], *dsy = h->tmB[0];
+    CUDA_TRY(cudaMemcpyAsync(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dsy, sy.data(), sy.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int nk_save = h->g.nk;
+    h->g.nk = 1;
+    double *f2[2] = {dsx, dsy};
+    int rc = halo_update(h, f2, 2, 3, st);
+    h->g.nk = nk_save;
+    if (rc) return rc;
+    if ((rc = alloc_quickw(h->qw, g))) { set_error("quicker weights: allocation failed"); return MOM5ADV_ECUDA; }
+    LAUNCH(h, k_quicker_weights, dim3((g.ni + 1 + 127) / 128, g.nj + 1), 128, 0, st, g, dsx, dsy, h->qw);
+    // vertical weights on the host (nk values), OTA:1566-1578
+    std::vector<double> qz(2 * g.nk), zp(3 * g.nk), zn(3 * g.nk);
+    for (int k = 1; k <= g.nk; k++) {
+        const int kp2 = std::min(k + 2, g.nk), kp1 = std::min(k + 1, g.nk), km1 = std::max(k - 1, 1);
+        const double zm = G->dzt[km1 - 1], z0 = G->dzt[k - 1], z1 = G->dzt[kp1 - 1], z2 = G->dzt[kp2 - 1];
+        qz[(k - 1)] = z1 / (z1 + z0);
+        qz[(k - 1) + g.nk] = z0 / (z1 + z0);
+        zp[(k - 1)] = (z0 * z1) / (((zm + (2.0 * z0)) + z1) * (z0 + z1));
+        zp[(k - 1) + g.nk] = -((z0 * z1) / ((z0 + z1) * (zm + z0)));
+        zp[(k - 1) + 2 * g.nk] = (z0 * z1) / (((zm + (2.0 * z0)) + z1) * (zm + z0));
+        zn[(k - 1)] = (z0 * z1) / (((z0 + (2.0 * z1)) + z2) * (z1 + z2));
+        zn[(k - 1) + g.nk] = -((z0 * z1) / ((z1 + z2) * (z0 + z1)));
+        zn[(k - 1) + 2 * g.nk] = (z0 * z1) / (((z0 + (2.0 * z1)) + z2) * (z0 + z1));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->qw.quick_z, qz.data(), qz.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->qw.curv_zp, zp.data(), zp.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->qw.curv_zn, zn.data(), zn.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemsetAsync(dsx, 0, (size_t)g.tslab * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(dsy, 0, (size_t)g.tslab * sizeof(double), st));
+    return 0;
+}

@@ -1,0 +1,74 @@
+// halo.cuh -- halo update of halo-2 ("h2") scratch fields: the GPU replacement, for this path only, of
+// FMS mpp_update_domains / mpp_start|complete_update_domains (OTA:4213-4240, 4302-4343, 3912, 3970, 2566).
+//
+// Semantics restated from src/shared/mpp/include/mpp_do_update.h:57-78,186-293 and
+// mpp_domains_define.inc:4865-4885 (scalar at CENTER position):
+//   XUPDATE = E/W strips for j in the compute domain; YUPDATE = N/S strips for i in the compute domain;
+//   both = all eight directions.  Interior neighbour and cyclic wrap are plain copies; the folded north edge
+//   maps (i, nj+m) <- (ni+1-i, nj+1-m); a solid wall has no image and its halo is left untouched.
+// Every halo point's source is a COMPUTE-domain point of exactly one rank, so one round of messages
+// suffices and there is no ordering requirement between directions.
+//
+// Strips whose source is this rank (single-rank cyclic wrap, fold onto the same rank) are served by one
+// local copy kernel; the rest are packed per peer, exchanged with ncclSend/ncclRecv inside one group, and
+// unpacked.  All tracers of a call travel in one message per peer (the reference's `complete=` aggregation).
+#pragma once
+
+#include "mom5adv_internal.cuh"
+
+#define HALO_MAXMSG 24
+#define HALO_MAXF 16
+
+struct CopyDesc {
+    int si0, sj0, si1, sj1;   // source rectangle (local h2 indices) -- used by pack and local copy
+    int di0, dj0;             // destination rectangle origin        -- used by unpack and local copy
+    int w, h, flip;
+    long long off;            // element offset of this strip inside the packed buffer (per field-level block layout below)
+};
+
+struct CopyArgs {
+    int nmsg, nf, nk;
+    long long total;              // total elements = sum_m w*h*nk*nf
+    long long start[HALO_MAXMSG + 1];  // prefix of per-message element counts
+    CopyDesc d[HALO_MAXMSG];
+    double *f[HALO_MAXF];
+    double *buf;
+};
+
+// mode 0: local copy (src rect -> dst rect, same rank); 1: pack (src rect -> buf); 2: unpack (buf -> dst rect)
+template <int MODE>
+__global__ void k_halo(const Geom g, const CopyArgs a)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.total; e += (long long)gridDim.x * blockDim.x) {
+        int m = 0;
+        while (e >= a.start[m + 1]) m++;
+        const CopyDesc &d = a.d[m];
+        long long r = e - a.start[m];
+        const int p = (int)(r % d.w); r /= d.w;
+        const int q = (int)(r % d.h); r /= d.h;
+        const int k = (int)(r % a.nk) + 1;
+        const int n = (int)(r / a.nk);
+        // element (p,q) is enumerated in the SENDER's orientation
+        const int si = d.si0 + p, sj = d.sj0 + q;
+        const int di = d.flip ? d.di0 + (d.w - 1 - p) : d.di0 + p;
+        const int dj = d.flip ? d.dj0 + (d.h - 1 - q) : d.dj0 + q;
+        if (MODE == 0) a.f[n][t3(g, di, dj, k)] = a.f[n][t3(g, si, sj, k)];
+        if (MODE == 1) a.buf[d.off + (e - a.start[m])] = a.f[n][t3(g, si, sj, k)];
+        if (MODE == 2) a.f[n][t3(g, di, dj, k)] = a.buf[d.off + (e - a.start[m])];
+    }
+}
+
+// compute-domain copy between a data-domain array and an h2 field (tracer_quick / tmask staging)
+__global__ void k_d1_to_h2(const Geom g, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i <= g.ni) dst[t3(g, i, j, k)] = src[d3(g, i, j, k)];
+}
+
+__global__ void k_h2_to_mask(const Geom g, const double *__restrict__ src, uint8_t *__restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;   // -1..ni+2
+    const int j = (int)blockIdx.y - 1, k = blockIdx.z + 1;
+    if (i <= g.ni + 2) dst[m3(g, i, j, k)] = (src[t3(g, i, j, k)] != 0.0) ? 1 : 0;
+}

@@ -1,0 +1,260 @@
+// horz_vert_kernels.cuh -- quicker and first-order upwind flux paths (the schemes that share the dispatcher
+// with MDFL Sweby) + quicker_init weights.
+//
+// Reference (OTA = src/mom5/ocean_tracers/ocean_tracer_advect.F90):
+//   quicker_init                 OTA:1442-1586      horz_advect_tracer_quicker  OTA:2538-2653
+//   vert_advect_tracer_quicker   OTA:2981-3031      horz_advect_tracer_upwind   OTA:2238-2294
+//   vert_advect_tracer_upwind    OTA:2792-2824      dispatcher tail             OTA:1990-1996, 2162-2168
+// These paths are pure streaming (no divisions, ~30 flops per face): plain coalesced one-thread-per-point
+// kernels, lanes along i.
+#pragma once
+
+#include "mom5adv_internal.cuh"
+
+struct QuickW {   // device arrays; 2-D ones in data-domain layout with a trailing component index
+    double *quick_x, *quick_y;                       // (nxd, nyd, 2)
+    double *curv_xp, *curv_xn, *curv_yp, *curv_yn;   // (nxd, nyd, 3)
+    double *quick_z, *curv_zp, *curv_zn;             // (nk,2) (nk,3) (nk,3)
+};
+
+static int alloc_quickw(QuickW &q, const Geom &g)
+{
+    const size_t n2 = (size_t)g.slab;
+    double **p2[] = {&q.quick_x, &q.quick_y};
+    double **p3[] = {&q.curv_xp, &q.curv_xn, &q.curv_yp, &q.curv_yn};
+    for (auto p : p2) { if (cudaMalloc(p, 2 * n2 * sizeof(double)) != cudaSuccess) return 1; cudaMemset(*p, 0, 2 * n2 * sizeof(double)); }
+    for (auto p : p3) { if (cudaMalloc(p, 3 * n2 * sizeof(double)) != cudaSuccess) return 1; cudaMemset(*p, 0, 3 * n2 * sizeof(double)); }
+    if (cudaMalloc(&q.quick_z, 2 * g.nk * sizeof(double)) != cudaSuccess) return 1;
+    if (cudaMalloc(&q.curv_zp, 3 * g.nk * sizeof(double)) != cudaSuccess) return 1;
+    if (cudaMalloc(&q.curv_zn, 3 * g.nk * sizeof(double)) != cudaSuccess) return 1;
+    return 0;
+}
+static void free_quickw(QuickW &q)
+{
+    for (double *p : {q.quick_x, q.quick_y, q.curv_xp, q.curv_xn, q.curv_yp, q.curv_yn, q.quick_z, q.curv_zp, q.curv_zn})
+        if (p) cudaFree(p);
+}
+
+// OTA:1516-1564; dx, dy are one-level h2 fields (dxt_quick, dyt_quick)
+__global__ void k_quicker_weights(const Geom g, const double *__restrict__ dx, const double *__restrict__ dy, const QuickW q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni
+    const int j = blockIdx.y;                              // 0..nj
+    if (i > g.ni) return;
+    const size_t c = d2(g, i, j), n2 = (size_t)g.slab;
+    const double xm = dx[t3(g, i - 1, j, 1)], x0 = dx[t3(g, i, j, 1)], x1 = dx[t3(g, i + 1, j, 1)], x2 = dx[t3(g, i + 2, j, 1)];
+    const double ym = dy[t3(g, i, j - 1, 1)], y0 = dy[t3(g, i, j, 1)], y1 = dy[t3(g, i, j + 1, 1)], y2 = dy[t3(g, i, j + 2, 1)];
+    q.quick_x[c] = x1 / (x1 + x0);
+    q.quick_x[c + n2] = x0 / (x1 + x0);
+    q.quick_y[c] = y1 / (y1 + y0);
+    q.quick_y[c + n2] = y0 / (y1 + y0);
+    q.curv_xp[c] = (x0 * x1) / (((xm + (2.0 * x0)) + x1) * (x0 + x1));
+    q.curv_xp[c + n2] = -((x0 * x1) / ((x0 + x1) * (xm + x0)));
+    q.curv_xp[c + 2 * n2] = (x0 * x1) / (((xm + (2.0 * x0)) + x1) * (xm + x0));
+    q.curv_xn[c] = (x0 * x1) / (((x0 + (2.0 * x1)) + x2) * (x1 + x2));
+    q.curv_xn[c + n2] = -((x0 * x1) / ((x1 + x2) * (x0 + x1)));
+    q.curv_xn[c + 2 * n2] = (x0 * x1) / (((x0 + (2.0 * x1)) + x2) * (x0 + x1));
+    q.curv_yp[c] = (y0 * y1) / (((ym + (2.0 * y0)) + y1) * (y0 + y1));
+    q.curv_yp[c + n2] = -((y0 * y1) / ((y0 + y1) * (ym + y0)));
+    q.curv_yp[c + 2 * n2] = (y0 * y1) / (((ym + (2.0 * y0)) + y1) * (ym + y0));
+    q.curv_yn[c] = (y0 * y1) / (((y0 + (2.0 * y1)) + y2) * (y1 + y2));
+    q.curv_yn[c + n2] = -((y0 * y1) / ((y1 + y2) * (y0 + y1)));
+    q.curv_yn[c + 2 * n2] = (y0 * y1) / (((y0 + (2.0 * y1)) + y2) * (y0 + y1));
+}
+
+// ---- horizontal fluxes: thread (i,j,k), i = 0..ni, j = 0..nj; flux_x for j >= 1, flux_y for i >= 1 ----
+template <bool QUICKER>
+__global__ void __launch_bounds__(128)
+k_horz_flux(const Geom g, const QuickW q, const double *__restrict__ tmask, const uint8_t *__restrict__ mq,
+            const double *__restrict__ dyte, const double *__restrict__ dxtn, const double *__restrict__ Tm1,
+            const double *__restrict__ Tt, const double *__restrict__ tq, const double *__restrict__ tlimit, const int limit,
+            const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ fx, double *__restrict__ fy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z + 1;
+    if (i > g.ni) return;
+    const size_t c = d3(g, i, j, k), c2 = d2(g, i, j), n2 = (size_t)g.slab;
+    if (j >= 1) {   // east face of (i,j)
+        double f;
+        bool up = !QUICKER;
+        if (QUICKER && limit) up = (tlimit[c] == 1.0);
+        if (!up) {   // OTA:2592-2604
+            const double vel = dyte[c2] * u[c];
+            const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+            const size_t mi = m3(g, i, j, k), ti = t3(g, i, j, k);
+            const double m_m1 = mq[mi - 1] ? 1.0 : 0.0, m_0 = mq[mi] ? 1.0 : 0.0, m_1 = mq[mi + 1] ? 1.0 : 0.0, m_2 = mq[mi + 2] ? 1.0 : 0.0;
+            const double eastmsk = m_0 * (1.0 - m_m1), westmsk = m_1 * (1.0 - m_2);
+            const double t0 = tq[ti], t1 = tq[ti + 1];
+            f = ((vel * ((q.quick_x[c2] * Tt[c]) + (q.quick_x[c2 + n2] * Tt[c + 1]))) -
+                 (upos * (((q.curv_xp[c2] * t1) + (q.curv_xp[c2 + n2] * t0)) +
+                          (q.curv_xp[c2 + 2 * n2] * ((tq[ti - 1] * (1.0 - eastmsk)) + (t0 * eastmsk)))))) -
+                (uneg * (((q.curv_xn[c2] * ((tq[ti + 2] * (1.0 - westmsk)) + (t1 * westmsk))) + (q.curv_xn[c2 + n2] * t1)) +
+                         (q.curv_xn[c2 + 2 * n2] * t0)));
+        } else if (QUICKER) {   // OTA:2613-2620: vel = u (not dyte*u), upos = 0.5*(vel+|vel|)
+            const double vel = u[c];
+            const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+            f = ((dyte[c2] * ((upos * Tm1[c]) + (uneg * Tm1[c + 1]))) * tmask[c]) * tmask[c + 1];
+        } else {                // OTA:2261-2265: velocity = 0.5*u, upos = velocity+|velocity|
+            const double velocity = 0.5 * u[c];
+            const double upos = velocity + fabs(velocity), uneg = velocity - fabs(velocity);
+            f = ((dyte[c2] * ((upos * Tm1[c]) + (uneg * Tm1[c + 1]))) * tmask[c]) * tmask[c + 1];
+        }
+        fx[c] = f;
+    }
+    if (i >= 1) {   // north face of (i,j)
+        double f;
+        bool up = !QUICKER;
+        if (QUICKER && limit) up = (tlimit[c] == 1.0);
+        if (!up) {   // OTA:2574-2586
+            const double vel = dxtn[c2] * v[c];
+            const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+            const size_t mi = m3(g, i, j, k), ti = t3(g, i, j, k);
+            const size_t mp = g.mpitch, tp = g.tpitch;
+            const double m_m1 = mq[mi - mp] ? 1.0 : 0.0, m_0 = mq[mi] ? 1.0 : 0.0, m_1 = mq[mi + mp] ? 1.0 : 0.0, m_2 = mq[mi + 2 * mp] ? 1.0 : 0.0;
+            const double rnormsk = m_0 * (1.0 - m_m1), soutmsk = m_1 * (1.0 - m_2);
+            const double t0 = tq[ti], t1 = tq[ti + tp];
+            f = ((vel * ((q.quick_y[c2] * Tt[c]) + (q.quick_y[c2 + n2] * Tt[c + g.nxd]))) -
+                 (upos * (((q.curv_yp[c2] * t1) + (q.curv_yp[c2 + n2] * t0)) +
+                          (q.curv_yp[c2 + 2 * n2] * ((tq[ti - tp] * (1.0 - rnormsk)) + (t0 * rnormsk)))))) -
+                (uneg * (((q.curv_yn[c2] * ((tq[ti + 2 * tp] * (1.0 - soutmsk)) + (t1 * soutmsk))) + (q.curv_yn[c2 + n2] * t1)) +
+                         (q.curv_yn[c2 + 2 * n2] * t0)));
+        } else if (QUICKER) {   // OTA:2625-2631
+            const double vel = v[c];
+            const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+            f = ((dxtn[c2] * ((upos * Tm1[c]) + (uneg * Tm1[c + g.nxd]))) * tmask[c]) * tmask[c + g.nxd];
+        } else {                // OTA:2273-2277
+            const double velocity = 0.5 * v[c];
+            const double upos = velocity + fabs(velocity), uneg = velocity - fabs(velocity);
+            f = ((dxtn[c2] * ((upos * Tm1[c]) + (uneg * Tm1[c + g.nxd]))) * tmask[c]) * tmask[c + g.nxd];
+        }
+        fy[c] = f;
+    }
+}
+
+// OTA:2640 on a rank that spans the whole fold line: flux_y(i, nj) := -flux_y(ni+1-i, nj) for i >= ni/2+1
+// (MPPI/mpp_domains_define.inc:1617,2535-2549; see oracle/mom5adv_oracle.c:orc_fold_fix_flux)
+__global__ void k_fold_fix(const Geom g, double *__restrict__ fy)
+{
+    const int middle = (1 + g.ni) / 2 + 1;
+    const int i = middle + blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y + 1;
+    if (i > g.ni) return;
+    fy[d3(g, i, g.nj, k)] = -fy[d3(g, g.ni + 1 - i, g.nj, k)];
+}
+
+// OTA:2642-2649 == 2282-2287, negated by the dispatcher (OTA:1936-1949), + th_tendency += wrk1 (OTA:1990-1996)
+// and the zeroing of wrk1 over the data domain (OTA:1925-1931): thread (i,j,k) over the whole data domain.
+__global__ void __launch_bounds__(128)
+k_horz_div(const Geom g, const double *__restrict__ tmask, const double *__restrict__ datr, const double *__restrict__ fx,
+           const double *__restrict__ fy, double *__restrict__ th, double *__restrict__ wrk1)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni+1
+    const int j = blockIdx.y, k = blockIdx.z + 1;          // 0..nj+1
+    if (i > g.ni + 1) return;
+    const size_t c = d3(g, i, j, k);
+    if (i < 1 || i > g.ni || j < 1 || j > g.nj) { wrk1[c] = 0.0; return; }
+    const double r = (tmask[c] * (((fx[c] - fx[c - 1]) + fy[c]) - fy[c - g.nxd])) * datr[d2(g, i, j)];
+    const double w = -r;
+    wrk1[c] = w;
+    th[c] = th[c] + w;
+}
+
+static int horz_upwind_dev(const Geom &g, const double *tmask, const double *dyte, const double *dxtn, const double *datr,
+                           const double *T, const double *u, const double *v, double *th, double *wrk1, double *fx, double *fy,
+                           cudaStream_t st, int64_t *launches)
+{
+    if (!fx || !fy) { set_error("upwind: flux_x and flux_y work arrays are required"); return -1; }
+    QuickW none{};
+    dim3 gf((g.ni + 1 + 127) / 128, g.nj + 1, g.nk);
+    k_horz_flux<false><<<gf, 128, 0, st>>>(g, none, tmask, nullptr, dyte, dxtn, T, nullptr, nullptr, nullptr, 0, u, v, fx, fy);
+    dim3 gd((g.ni + 2 + 127) / 128, g.nj + 2, g.nk);
+    k_horz_div<<<gd, 128, 0, st>>>(g, tmask, datr, fx, fy, th, wrk1);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int horz_quicker_dev(const Geom &g, const QuickW &q, const double *tmask, const uint8_t *mq, const double *dyte,
+                            const double *dxtn, const double *datr, const double *Tm1, const double *Tt, const double *tq,
+                            const double *tlimit, int limit, const double *u, const double *v, double *th, double *wrk1,
+                            double *fx, double *fy, int tripolar, int ni_g, int isc_g, bool top_row, cudaStream_t st,
+                            int64_t *launches)
+{
+    // flux_x = flux_y = 0 (OTA:2568-2569)
+    const size_t bytes = (size_t)g.slab * g.nk * sizeof(double);
+    if (cudaMemsetAsync(fx, 0, bytes, st) != cudaSuccess || cudaMemsetAsync(fy, 0, bytes, st) != cudaSuccess) return -2;
+    dim3 gf((g.ni + 1 + 127) / 128, g.nj + 1, g.nk);
+    k_horz_flux<true><<<gf, 128, 0, st>>>(g, q, tmask, mq, dyte, dxtn, Tm1, Tt, tq, tlimit, limit, u, v, fx, fy);
+    *launches += 1;
+    if (tripolar && top_row) {
+        if (g.ni != ni_g || isc_g != 1) return -100;   // fold line split across ranks
+        const int n = g.ni - ((1 + g.ni) / 2 + 1) + 1;
+        if (n > 0) {
+            k_fold_fix<<<dim3((n + 127) / 128, g.nk), 128, 0, st>>>(g, fy);
+            *launches += 1;
+        }
+    }
+    dim3 gd((g.ni + 2 + 127) / 128, g.nj + 2, g.nk);
+    k_horz_div<<<gd, 128, 0, st>>>(g, tmask, datr, fx, fy, th, wrk1);
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- vertical: one thread per column marching down k (ft1 carried in a register) ----
+template <bool QUICKER>
+__global__ void __launch_bounds__(128)
+k_vert(const Geom g, const QuickW q, const double *__restrict__ tmask, const double *__restrict__ dat,
+       const double *__restrict__ Tm1, const double *__restrict__ Tt, const double *__restrict__ tlimit,
+       const double *__restrict__ w, double *__restrict__ th, double *__restrict__ wrk1, double *__restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni+1 (halo ring columns only zero wrk1)
+    const int j = blockIdx.y;
+    if (i > g.ni + 1) return;
+    if (i < 1 || i > g.ni || j < 1 || j > g.nj) {          // OTA:2116-2122
+        for (int k = 1; k <= g.nk; k++) wrk1[d3(g, i, j, k)] = 0.0;
+        return;
+    }
+    const double da = dat[d2(g, i, j)];
+    double ft1 = 0.0;
+    for (int k = 1; k <= g.nk; k++) {
+        const int km1 = max(k - 1, 1), kp1 = min(k + 1, g.nk), p2 = min(k + 2, g.nk);
+        const size_t c = d3(g, i, j, k), cp1 = d3(g, i, j, kp1);
+        double ft2;
+        if (!QUICKER) {          // OTA:2810-2814
+            const double velocity = 0.5 * w[w3(g, i, j, k)];
+            const double wpos = velocity + fabs(velocity), wneg = velocity - fabs(velocity);
+            ft2 = (((wneg * Tm1[c]) + (wpos * Tm1[cp1])) * tmask[c]) * tmask[cp1];
+        } else {
+            const double vel = w[w3(g, i, j, k)];
+            const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+            if (tlimit[c] == 1.0) {   // OTA:3006-3008
+                ft2 = (((uneg * Tm1[c]) + (upos * Tm1[cp1])) * tmask[c]) * tmask[cp1];
+            } else {                  // OTA:3010-3019
+                const double mp2 = tmask[d3(g, i, j, p2)];
+                const int kp2 = (int)llround((mp2 * (double)p2) + ((1.0 - mp2) * (double)kp1));
+                const double upmsk = tmask[c] * (1.0 - tmask[d3(g, i, j, km1)]);
+                const int nk = g.nk;
+                ft2 = ((vel * ((q.quick_z[k - 1] * Tt[c]) + (q.quick_z[k - 1 + nk] * Tt[cp1]))) -
+                       (uneg * (((q.curv_zp[k - 1] * Tm1[cp1]) + (q.curv_zp[k - 1 + nk] * Tm1[c])) +
+                                (q.curv_zp[k - 1 + 2 * nk] * Tm1[d3(g, i, j, km1)])))) -
+                      (upos * (((q.curv_zn[k - 1] * Tm1[d3(g, i, j, kp2)]) + (q.curv_zn[k - 1 + nk] * Tm1[cp1])) +
+                               (q.curv_zn[k - 1 + 2 * nk] * ((Tm1[c] * (1.0 - upmsk)) + (Tm1[cp1] * upmsk)))));
+            }
+        }
+        if (fz) fz[c] = da * ft2;
+        const double wv = -(tmask[c] * (ft1 - ft2));
+        wrk1[c] = wv;
+        th[c] = th[c] + wv;          // OTA:2162-2168
+        ft1 = ft2;
+    }
+}
+
+static int vert_dev(const Geom &g, const QuickW &q, const double *tmask, const double *dat, const double *Tm1, const double *Tt,
+                    const double *tlimit, const double *w, double *th, double *wrk1, double *fz, int quicker, cudaStream_t st,
+                    int64_t *launches)
+{
+    dim3 grid((g.ni + 2 + 127) / 128, g.nj + 2);
+    if (quicker) k_vert<true><<<grid, 128, 0, st>>>(g, q, tmask, dat, Tm1, Tt, tlimit, w, th, wrk1, fz);
+    else k_vert<false><<<grid, 128, 0, st>>>(g, q, tmask, dat, Tm1, Tt, tlimit, w, th, wrk1, fz);
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

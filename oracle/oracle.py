@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -203,17 +204,23 @@ class Oracle:
         return out
 
     def sweby_all_timed(self, T, th, dtime: float, nthreads: int = 0):
-        """Whole call through the C multi-block driver (OpenMP over blocks): the timed CPU baseline."""
+        """Whole call through the C multi-block driver (OpenMP over blocks): the timed CPU baseline.
+        Scratch (tm, adv) is allocated once per tracer count and reused, as the reference's module arrays are."""
         if not self._mdfl_ready:
             self.mdfl_init()
         nb, ntr = self.nb, len(T[0])
-        tm = [[b.h2() for _ in range(ntr)] for b in self.blocks]
-        adv = [[b.d1() for _ in range(ntr)] for b in self.blocks]
+        if getattr(self, "_timed_ntr", None) != ntr:
+            self._tm = [[b.h2() for _ in range(ntr)] for b in self.blocks]
+            self._adv = [[b.d1() for _ in range(ntr)] for b in self.blocks]
+            self._timed_ntr = ntr
+        tm, adv = self._tm, self._adv
         flat = lambda xs: _pp([a for xb in xs for a in xb])
         args = (C.byref(self.layout), self._carr, C.c_int(ntr), C.c_double(dtime), flat(T), _pp(self.u), _pp(self.v),
                 _pp(self.w), _pp(self.rho), flat(tm), flat(th), flat(adv), C.c_int(nthreads))
+        t0 = time.perf_counter()
         self.L.orc_sweby_all_multiblock(*args)
-        return dict(adv=adv, tm=tm, _args=args)
+        self.last_seconds = time.perf_counter() - t0
+        return dict(adv=adv, tm=tm)
 
     # ---- advect_tracer_mdfl_sweby (one tracer) ----
     def mdfl_sweby(self, T: List[np.ndarray], dtime: float, sweby_limiter: float = 1.0):

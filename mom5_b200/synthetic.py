@@ -87,6 +87,7 @@ class CaseSpec:
     dtime: float = 3600.0
     cfl: float = 0.5            # target max directional CFL
     seed: int = 20240601
+    rho_noise: float = 0.01     # relative cell-to-cell variation of rho_dzt
     flow_scale: Optional[float] = None  # set by calibrate(); None -> computed on first use (needs the global max)
 
     @property
@@ -264,13 +265,13 @@ class Generator:
         h = (0.55 + 0.30 * torch.sin(3 * x + 0.7) * torch.sin(2 * y + 0.3) + 0.22 * torch.cos(5 * x - 1.1) * torch.cos(3 * y)
              + 0.10 * (self._noise(_FID["kmt"], ig, jg) - 0.5))
         land = h < 0.42
-        lev = torch.round(s.nk * (0.25 + 0.9 * (h - 0.42))).to(I64).clamp(2, s.nk)
+        lev = torch.round(s.nk * (0.25 + 1.4 * (h - 0.42))).to(I64).clamp(2, s.nk)
         return torch.where(valid & ~land, lev, torch.zeros_like(lev))
 
     # ---- 3-D fields ------------------------------------------------------------------------------
     def rho_dzt(self, ig, jg, k):
         igs, jgs, _ = self._src(ig, jg)
-        return RHO0 * self.dzt[k - 1] * (1.0 + 0.01 * (2.0 * self._noise(_FID["rho"], igs, jgs, k) - 1.0))
+        return RHO0 * self.dzt[k - 1] * (1.0 + self.s.rho_noise * (2.0 * self._noise(_FID["rho"], igs, jgs, k) - 1.0))
 
     def _face_amp(self, fid, ig, jg, a, b, ph):
         s = self.s

@@ -1,0 +1,73 @@
+"""The C-ABI library must load without a GPU and export every symbol include/mom5adv.h declares (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from mom5_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "mom5adv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mom5adv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    from mom5_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    assert lib.mom5adv_version() == 100
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    names = declared_functions()
+    assert len(names) >= 18
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} declared in include/mom5adv.h but not exported"
+        assert nm in _lib.SYMBOLS, f"{nm} has no ctypes signature in mom5_b200/_lib.py"
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_no_link_time_dependency_on_nccl_or_torch():
+    """NCCL is dlopen'ed on first use so that a host process keeps its own copy (PyTorch bundles one)."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "nccl" not in out and "torch" not in out
+
+
+def test_sass_is_sm100a_fp64_without_fma_contraction():
+    """the bit-exact build: sm_100a SASS, DADD/DMUL present, and no DFMA in the sweep kernels other than the
+    ones inside the IEEE division sequences (those are correctly-rounded by construction)"""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_init_without_gpu_or_bad_args_fails_loudly():
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.mom5adv_init(None, 1, None, C.byref(h))
+    assert rc == -1 and b"bad arguments" in lib.mom5adv_last_error()
+    g = _lib.Grid()
+    g.have_obc = 1
+    rc = lib.mom5adv_init(C.byref(g), 1, None, C.byref(h))
+    assert rc == -5 and b"open boundaries" in lib.mom5adv_last_error()
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        g.have_obc = 0
+        rc = lib.mom5adv_init(C.byref(g), 1, None, C.byref(h))
+        assert rc == -4 and b"no CUDA device" in lib.mom5adv_last_error()   # no silent CPU fallback

@@ -86,7 +86,8 @@ struct mom5adv_ctx {
     int ntr_max = 0;
     // static device data
     double *dat = 0, *datr = 0, *dxte = 0, *dyte = 0, *dxtn = 0, *dytn = 0, *tmask = 0;
-    uint8_t *mask = 0;
+    uint8_t *mask = 0;                 // tmask_mdfl == tmask_quick as u8, halo 2
+    uint8_t *nibz = 0, *nibx = 0, *niby = 0;   // per-direction neighbourhood nibbles, data-domain layout
     QuickW qw{};                       // quicker weights (device)
     std::vector<double *> tmA, tmB;    // h2 scratch per tracer
     // halo machinery
@@ -516,6 +517,10 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     if ((rc = halo_update(h, f0, 1, 3, st))) { return rc; }
     dim3 gm((g.ni + 4 + 127) / 128, g.nj + 4, g.nk);
     LAUNCH(h, k_h2_to_mask, gm, 128, 0, st, g, h->tmA[0], h->mask);
+    CUDA_TRY(cudaMalloc(&h->nibz, n3(h)));
+    CUDA_TRY(cudaMalloc(&h->nibx, n3(h)));
+    CUDA_TRY(cudaMalloc(&h->niby, n3(h)));
+    LAUNCH(h, k_build_nibbles, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, h->mask, h->nibz, h->nibx, h->niby);
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaMemset(h->tmA[0], 0, nh2(h) * sizeof(double)));
     if ((rc = quicker_setup(h, G, st))) return rc;
@@ -531,7 +536,8 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
     cudaDeviceSynchronize();
     for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w})
         if (p) cudaFree(p);
-    if (h->mask) cudaFree(h->mask);
+    for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
+        if (p) cudaFree(p);
     for (double *p : h->tmA) cudaFree(p);
     for (double *p : h->tmB) cudaFree(p);
     for (double *p : h->hm) cudaFree(p);
@@ -561,12 +567,12 @@ static void launch_group(mom5adv_ctx *h, int phase, const SwebyArgs<NT> &a, cuda
     SwebyArgs<NT> b = a;
     if (phase == 0) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
-        dim3 grid((g.ni + ZBX - 1) / ZBX, (g.nj + ZBY - 1) / ZBY, (g.nk + b.kc - 1) / b.kc);
-        LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, dim3(ZBX, ZBY), 0, st, g, b);
+        dim3 grid((g.ni + ZBX - 1) / ZBX, g.nj, (g.nk + b.kc - 1) / b.kc);
+        LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, ZBX, 0, st, g, b);
     } else if (phase == 1) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
-        dim3 grid((g.ni + 1 + XBX - 2) / (XBX - 1), (g.nj + XBY - 1) / XBY, (g.nk + b.kc - 1) / b.kc);
-        LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(XBX, XBY), 0, st, g, b);
+        dim3 grid((g.ni + 30) / 31, (g.nj + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
+        LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(32, XWARPS), 0, st, g, b);
     } else {
         const int nxt = (g.ni + YBX - 1) / YBX;
         const long long per_chunk = (long long)nxt * YBX * g.nk;
@@ -604,7 +610,8 @@ static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cud
         a.dadv[n] = da ? da[n0 + n] : nullptr;
         diag |= (a.flux[n] != nullptr) || (a.dadv[n] != nullptr);
     }
-    a.u = c.u; a.v = c.v; a.w = c.w; a.rho = c.rho; a.mask = h->mask;
+    a.u = c.u; a.v = c.v; a.w = c.w; a.rho = c.rho;
+    a.nib = phase == 0 ? h->nibz : phase == 1 ? h->nibx : h->niby;
     a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
     a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;
     if (c.var == VAR_ALL) {

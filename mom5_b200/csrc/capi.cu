@@ -574,6 +574,7 @@ static void launch_group(mom5adv_ctx *h, int phase, const SwebyArgs<NT> &a, cuda
         dim3 grid((g.ni + 30) / 31, (g.nj + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(32, XWARPS), 0, st, g, b);
     } else {
+        const int YBX = 32 * YWARPS;
         const int nxt = (g.ni + YBX - 1) / YBX;
         const long long per_chunk = (long long)nxt * YBX * g.nk;
         int rows = 32;

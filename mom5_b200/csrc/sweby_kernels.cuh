@@ -46,10 +46,58 @@ struct SwebyArgs {
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- per-thread asynchronous staging (LDGSTS): global -> shared one iteration ahead, no register cost ----
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Each sweep's arithmetic for ONE stencil level lives in a `*_level<..., EXACT>` function working on a small
+// struct of per-thread operands.  The kernels run the EXACT=false flavour (shared reciprocals, branch-free); if any of
+// its division guards fails (`bad`), the level is redone by the out-of-line EXACT=true flavour (plain `/`).
+
 // =================================================================================================
 // z sweep  (OTA:4150-4211 / 3843-3911)
 // =================================================================================================
 #define ZBX 128
+
+template <int NT>
+struct ZLevel {
+    double dat, datr, wk, wkm1, r, dtime, sl;
+    unsigned nb;
+    double Tk[NT], Tp1[NT], Tp2[NT], Rm1[NT], R0[NT], ftp[NT];   // in
+    double fbt[NT], Rp1[NT], t[NT], wz[NT];                        // out
+};
+
+template <int NT, int VAR, bool EXACT>
+__device__ __forceinline__ unsigned z_level(ZLevel<NT> &L)
+{
+    unsigned bad = 0;
+    const Div<EXACT> rr(L.r, bad);
+    const FaceCoef c = make_coef<EXACT>(L.dat * L.wk, fabs(rr(L.wk * L.dtime, bad)), nib_and(L.nb, 6u), bad);
+    const double mm12 = nib_and(L.nb, 12u);           // m(kp1)*m(kp2)
+    const double dtr = (VAR == VAR_ONE) ? rr(L.dtime, bad) : 0.0;
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+        L.Rp1[n] = (L.Tp1[n] - L.Tp2[n]) * mm12;
+        const double fbt = sweby_flux<VAR, EXACT>(c, L.Rm1[n], L.R0[n], L.Rp1[n], L.Tp1[n], L.Tk[n], L.sl, bad);
+        L.fbt[n] = fbt;
+        if (VAR == VAR_ALL) {  // OTA:4191-4195
+            L.wz[n] = (L.datr * (fbt - L.ftp[n])) + (L.Tk[n] * (L.wkm1 - L.wk));
+            L.t[n] = L.Tk[n] + rr(L.wz[n] * L.dtime, bad);
+        } else {               // OTA:3892-3896
+            L.wz[n] = 0.0;
+            L.t[n] = L.Tk[n] + (dtr * ((L.datr * (fbt - L.ftp[n])) + (L.Tk[n] * (L.wkm1 - L.wk))));
+        }
+    }
+    return bad;
+}
+template <int NT, int VAR>
+__device__ __noinline__ void z_level_exact(ZLevel<NT> *L) { z_level<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
 __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArgs<NT> a)
@@ -60,9 +108,7 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
     const int k0 = ks > 1 ? ks - 1 : 1;  // first face evaluated (warm-up face when the chunk starts below the surface)
-    const double dtime = a.dtime;
     const size_t c2 = d2(g, i, j);
-    const double dat = a.dat[c2], datr = a.datr[c2];
     const size_t slab = (size_t)g.slab;
 
     size_t qd = d3(g, i, j, k0);                                  // data-domain offset of level k
@@ -70,22 +116,24 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
     size_t q2 = qd + slab * (size_t)(min(k0 + 2, g.nk) - k0);     // data-domain offset of level min(k+2, nk)
     const size_t qkm = (k0 > 1) ? qd - slab : qd, qkp = (k0 < g.nk) ? qd + slab : qd;
 
-    unsigned nb = a.nib[qd];
-    double Tk[NT], Tp1[NT], Rm1[NT], R0[NT], ftp[NT], Tp2[NT];
+    ZLevel<NT> L;
+    L.dat = a.dat[c2]; L.datr = a.datr[c2]; L.dtime = a.dtime; L.sl = a.sl;
+    L.nb = a.nib[qd];
 #pragma unroll
     for (int n = 0; n < NT; n++) {
         const double Tkm = a.T[n][qkm];
-        Tk[n] = a.T[n][qd];
-        Tp1[n] = a.T[n][qkp];
-        Tp2[n] = a.T[n][q2];
-        Rm1[n] = (Tkm - Tk[n]) * nib_and(nb, 3u);      // ((T(km1)-T(k))*m(km1))*m(k); +0 at k = 1 (km1 clamps)
-        R0[n] = (Tk[n] - Tp1[n]) * nib_and(nb, 6u);    // ((T(k)-T(kp1))*m(k))*m(kp1)
-        ftp[n] = 0.0;
+        L.Tk[n] = a.T[n][qd];
+        L.Tp1[n] = a.T[n][qkp];
+        L.Tp2[n] = a.T[n][q2];
+        L.Rm1[n] = (Tkm - L.Tk[n]) * nib_and(L.nb, 3u);      // ((T(km1)-T(k))*m(km1))*m(k); +0 at k = 1 (km1 clamps)
+        L.R0[n] = (L.Tk[n] - L.Tp1[n]) * nib_and(L.nb, 6u);  // ((T(k)-T(kp1))*m(k))*m(kp1)
+        L.ftp[n] = 0.0;
     }
-    double wkm1 = 0.0;
-    double wk = a.w[qd + slab];                         // w3(k) = d3(k) + slab
-    double r = a.rho[qd];
+    L.wkm1 = 0.0;
+    L.wk = a.w[qd + slab];                               // w3(k) = d3(k) + slab
+    L.r = a.rho[qd];
 
+#pragma unroll 3
     for (int k = k0; k <= ke; k++) {
         // ---- software pipeline: operands of level k+1 ----
         const bool more = (k < ke);
@@ -103,58 +151,96 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
             for (int n = 0; n < NT; n++) Tp2_n[n] = a.T[n][q2_n];
         }
         // ---- level k ----
-        const Rcp rr = make_rcp(r);
-        const FaceCoef c = make_coef(dat * wk, fabs(div_rcp(wk * dtime, rr)), nib_and(nb, 6u));
-        const double mm12 = nib_and(nb, 12u);           // m(kp1)*m(kp2)
+        if (z_level<NT, VAR, false>(L)) {
+            ZLevel<NT> X = L;
+            z_level_exact<NT, VAR>(&X);
+#pragma unroll
+            for (int n = 0; n < NT; n++) { L.fbt[n] = X.fbt[n]; L.Rp1[n] = X.Rp1[n]; L.t[n] = X.t[n]; L.wz[n] = X.wz[n]; }
+        }
         const bool live = (k >= ks);
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-            const double Rp1 = (Tp1[n] - Tp2[n]) * mm12;
-            const double fbt = sweby_flux<VAR>(c, Rm1[n], R0[n], Rp1, Tp1[n], Tk[n], a.sl);
             if (live) {
-                double t;
-                if (VAR == VAR_ALL) {  // OTA:4191-4195
-                    const double wz = (datr * (fbt - ftp[n])) + (Tk[n] * (wkm1 - wk));
-                    t = Tk[n] + div_rcp(wz * dtime, rr);
-                    if (DIAG && a.dadv[n]) a.dadv[n][qd] = wz;
-                } else {               // OTA:3892-3896
-                    t = Tk[n] + (div_rcp(dtime, rr) * ((datr * (fbt - ftp[n])) + (Tk[n] * (wkm1 - wk))));
-                }
-                a.tm_in[n][qt] = t;
-                if (DIAG && a.flux[n]) a.flux[n][qd] = fbt;
+                a.tm_in[n][qt] = L.t[n];
+                if (DIAG && VAR == VAR_ALL && a.dadv[n]) a.dadv[n][qd] = L.wz[n];
+                if (DIAG && a.flux[n]) a.flux[n][qd] = L.fbt[n];
             }
-            ftp[n] = fbt;
-            Rm1[n] = R0[n];
-            R0[n] = Rp1;
-            Tk[n] = Tp1[n];
-            Tp1[n] = Tp2[n];
-            Tp2[n] = Tp2_n[n];
+            L.ftp[n] = L.fbt[n];
+            L.Rm1[n] = L.R0[n];
+            L.R0[n] = L.Rp1[n];
+            L.Tk[n] = L.Tp1[n];
+            L.Tp1[n] = L.Tp2[n];
+            L.Tp2[n] = Tp2_n[n];
         }
-        wkm1 = wk;
-        wk = wk_n;
-        r = r_n;
-        nb = nb_n;
+        L.wkm1 = L.wk;
+        L.wk = wk_n;
+        L.r = r_n;
+        L.nb = nb_n;
         qd = qd_n;
         q2 = q2_n;
         qt += (size_t)g.tslab;
     }
 }
 
-// ---- per-thread asynchronous staging (LDGSTS): global -> shared one iteration ahead, no register cost ----
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // =================================================================================================
 // x sweep  (OTA:4251-4299 / 3916-3969)
 // =================================================================================================
 #define XWARPS 4    // warps per block, stacked along j
 #define XROW 36     // staged row: tm(i_w-1 .. i_w+33) = 35 values (+1 pad)
+
+template <int NT>
+struct XFace {   // east face of (i,j,k)
+    double dyte, dxte, uu, rho_i, rho_e, dtime, sl;
+    unsigned nb;
+    double tm1[NT], t0[NT], t1[NT], t2[NT];   // in
+    double mf, f[NT];                          // out
+};
+template <int NT, int VAR, bool EXACT>
+__device__ __forceinline__ unsigned x_face(XFace<NT> &L)
+{
+    unsigned bad = 0;
+    L.mf = L.dyte * L.uu;
+    const FaceCoef c = make_coef<EXACT>(L.mf, fabs(Div<EXACT>((L.rho_i + L.rho_e) * L.dxte, bad)((L.uu * L.dtime) * 2.0, bad)),
+                                        nib_and(L.nb, 6u), bad);
+    const double mm01 = nib_and(L.nb, 3u), mm23 = nib_and(L.nb, 12u);
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+        const double Rjp = (L.t2[n] - L.t1[n]) * mm23;      // ((tm(i+2)-tm(i+1))*m(i+2))*m(i+1)
+        const double Rj = (L.t1[n] - L.t0[n]) * c.mm;       // ((tm(i+1)-tm(i))*m(i+1))*m(i)
+        const double Rjm = (L.t0[n] - L.tm1[n]) * mm01;     // ((tm(i)-tm(i-1))*m(i))*m(i-1)
+        L.f[n] = sweby_flux<VAR, EXACT>(c, Rjp, Rj, Rjm, L.t0[n], L.t1[n], L.sl, bad);
+    }
+    return bad;
+}
+template <int NT, int VAR>
+__device__ __noinline__ void x_face_exact(XFace<NT> *L) { x_face<NT, VAR, true>(*L); }
+
+template <int NT>
+struct XCell {   // cell (i,j,k)
+    double m_i, datr, rho_i, dtime, mf, mfw;
+    double f[NT], fw[NT], Tc[NT], t0[NT];     // in
+    double t[NT], wx[NT];                      // out
+};
+template <int NT, int VAR, bool EXACT>
+__device__ __forceinline__ unsigned x_cell(XCell<NT> &L)
+{
+    unsigned bad = 0;
+    const Div<EXACT> rr(L.rho_i, bad);
+    const double coef = (VAR == VAR_ONE) ? rr((L.dtime * L.m_i) * L.datr, bad) : 0.0;
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+        if (VAR == VAR_ALL) {  // OTA:4288-4295
+            L.wx[n] = (L.m_i * L.datr) * ((L.fw[n] - L.f[n]) + (L.Tc[n] * (L.mf - L.mfw)));
+            L.t[n] = L.t0[n] + rr(L.wx[n] * L.dtime, bad);
+        } else {               // OTA:3960-3965
+            L.wx[n] = 0.0;
+            L.t[n] = L.t0[n] + (coef * ((L.fw[n] - L.f[n]) + (L.Tc[n] * (L.mf - L.mfw))));
+        }
+    }
+    return bad;
+}
+template <int NT, int VAR>
+__device__ __noinline__ void x_cell_exact(XCell<NT> *L) { x_cell<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
 __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const SwebyArgs<NT> a)
@@ -171,9 +257,11 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
     const int ic = min(i, g.ni);                         // clamped index for the loads of idle lanes
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
-    const double dtime = a.dtime;
     const size_t c2 = d2(g, ic, j);
-    const double dyte = a.dyte[c2], dxte = a.dxte[c2], datr = a.datr[c2];
+    XFace<NT> F;
+    XCell<NT> C;
+    F.dyte = a.dyte[c2]; F.dxte = a.dxte[c2]; F.dtime = a.dtime; F.sl = a.sl;
+    C.datr = a.datr[c2]; C.dtime = a.dtime;
     const size_t slab = (size_t)g.slab, tslab = (size_t)g.tslab;
     size_t q = d3(g, ic, j, ks);
     // staged elements: tm element e = iw-1+lane (slot lane) and, for lanes 0..2, iw+31+lane (slot 32+lane);
@@ -211,35 +299,40 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
         cp_async_wait<1>();
         __syncwarp();
         double(*S)[XROW] = sm[st][wy];
-        const double m_i = nib_and(nb, 2u);
-        const double uu = S[2 * NT][lane];
-        const double rho_i = S[2 * NT + 1][lane];
-        const double rho_e = S[2 * NT + 1][lane + 1];
-        const double mf = dyte * uu;
-        const FaceCoef c = make_coef(mf, fabs(div_rcp((uu * dtime) * 2.0, make_rcp((rho_i + rho_e) * dxte))), nib_and(nb, 6u));
-        const double mm01 = nib_and(nb, 3u), mm23 = nib_and(nb, 12u);
-        const Rcp rr = make_rcp(rho_i);
-        const double mfw = __shfl_up_sync(0xffffffffu, mf, 1);
+        F.nb = nb;
+        F.uu = S[2 * NT][lane];
+        F.rho_i = S[2 * NT + 1][lane];
+        F.rho_e = S[2 * NT + 1][lane + 1];
+#pragma unroll
+        for (int n = 0; n < NT; n++) { F.tm1[n] = S[n][lane]; F.t0[n] = S[n][lane + 1]; F.t1[n] = S[n][lane + 2]; F.t2[n] = S[n][lane + 3]; }
+        if (x_face<NT, VAR, false>(F)) {
+            XFace<NT> X = F;
+            x_face_exact<NT, VAR>(&X);
+            F.mf = X.mf;
+#pragma unroll
+            for (int n = 0; n < NT; n++) F.f[n] = X.f[n];
+        }
+        C.m_i = nib_and(nb, 2u); C.rho_i = F.rho_i; C.mf = F.mf;
+        C.mfw = __shfl_up_sync(0xffffffffu, F.mf, 1);
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-            const double tm1 = S[n][lane], t0 = S[n][lane + 1], t1 = S[n][lane + 2], t2 = S[n][lane + 3];
-            const double Rjp = (t2 - t1) * mm23;      // ((tm(i+2)-tm(i+1))*m(i+2))*m(i+1)
-            const double Rj = (t1 - t0) * c.mm;       // ((tm(i+1)-tm(i))*m(i+1))*m(i)
-            const double Rjm = (t0 - tm1) * mm01;     // ((tm(i)-tm(i-1))*m(i))*m(i-1)
-            const double f = sweby_flux<VAR>(c, Rjp, Rj, Rjm, t0, t1, a.sl);
-            const double fw = __shfl_up_sync(0xffffffffu, f, 1);
-            if (DIAG && face_ok && a.flux[n]) a.flux[n][q_cur] = f;
-            if (cell_ok) {
-                const double Tc = S[NT + n][lane];
-                double t;
-                if (VAR == VAR_ALL) {  // OTA:4288-4295
-                    const double wx = (m_i * datr) * ((fw - f) + (Tc * (mf - mfw)));
-                    t = t0 + div_rcp(wx * dtime, rr);
-                    if (DIAG && a.dadv[n]) a.dadv[n][q_cur] = wx;
-                } else {               // OTA:3960-3965
-                    t = t0 + (div_rcp((dtime * m_i) * datr, rr) * ((fw - f) + (Tc * (mf - mfw))));
-                }
-                a.tm_out[n][tq_cur] = t;
+            C.f[n] = F.f[n];
+            C.fw[n] = __shfl_up_sync(0xffffffffu, F.f[n], 1);
+            C.Tc[n] = S[NT + n][lane];
+            C.t0[n] = F.t0[n];
+            if (DIAG && face_ok && a.flux[n]) a.flux[n][q_cur] = F.f[n];
+        }
+        if (cell_ok) {
+            if (x_cell<NT, VAR, false>(C)) {
+                XCell<NT> X = C;
+                x_cell_exact<NT, VAR>(&X);
+#pragma unroll
+                for (int n = 0; n < NT; n++) { C.t[n] = X.t[n]; C.wx[n] = X.wx[n]; }
+            }
+#pragma unroll
+            for (int n = 0; n < NT; n++) {
+                a.tm_out[n][tq_cur] = C.t[n];
+                if (DIAG && VAR == VAR_ALL && a.dadv[n]) a.dadv[n][q_cur] = C.wx[n];
             }
         }
         nb = nb_n;
@@ -251,6 +344,51 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
 // =================================================================================================
 #define YWARPS 4
 #define YROW 33     // staged row: element 0 = (i_w - 1), elements 1..32 = the lanes' own i
+
+template <int NT>
+struct YLevel {   // north face of (i,jf,k) and, when live, cell (i,jf,k)
+    double vv, rho0, rho1, dxtn, dytn, datr, wk, wkm1, dyte_w, u_w, dyte_c, u_c, dtime, sl;
+    unsigned nb;
+    int live;
+    double t0[NT], t1[NT], t2[NT], Rm1[NT], R0[NT], fprev[NT], Tc[NT];   // in
+    double f[NT], Rp1[NT], adv[NT], wy[NT];                                // out
+};
+template <int NT, int VAR, bool EXACT>
+__device__ __forceinline__ unsigned y_level(YLevel<NT> &L)
+{
+    unsigned bad = 0;
+    const double mf = L.dxtn * L.vv;
+    const FaceCoef c = make_coef<EXACT>(mf, fabs(Div<EXACT>((L.rho0 + L.rho1) * L.dytn, bad)((L.vv * L.dtime) * 2.0, bad)),
+                                        nib_and(L.nb, 6u), bad);
+    const double mm23 = nib_and(L.nb, 12u), m0 = nib_and(L.nb, 2u);
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+        L.Rp1[n] = (L.t2[n] - L.t1[n]) * mm23;   // ((tm(j+2)-tm(j+1))*m(j+2))*m(j+1)
+        L.f[n] = sweby_flux<VAR, EXACT>(c, L.Rp1[n], L.R0[n], L.Rm1[n], L.t0[n], L.t1[n], L.sl, bad);
+    }
+    if (L.live) {
+        // T*( (w(k)-wkm1) + datr*(dyte(i-1)*u(i-1) - dyte(i)*u(i)) )  (OTA:4402-4406)
+        const double wdiv = (L.wk - L.wkm1) + (L.datr * ((L.dyte_w * L.u_w) - (L.dyte_c * L.u_c)));
+        const Div<EXACT> rr(L.rho0, bad), rdt(L.dtime, bad);
+        const double c1 = (VAR == VAR_ONE) ? rr((L.dtime * m0) * L.datr, bad) : 0.0;
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+            double t;
+            if (VAR == VAR_ALL) {  // OTA:4401-4413
+                L.wy[n] = ((m0 * L.datr) * (L.fprev[n] - L.f[n])) + (L.Tc[n] * wdiv);
+                t = L.t0[n] + rr(L.wy[n] * L.dtime, bad);
+            } else {               // OTA:4025-4040
+                L.wy[n] = 0.0;
+                t = L.t0[n] + (c1 * (L.fprev[n] - L.f[n]));
+                t = t + (rr(L.dtime * L.Tc[n], bad) * wdiv);
+            }
+            L.adv[n] = rdt(L.rho0 * (t - L.Tc[n]), bad) * m0;
+        }
+    }
+    return bad;
+}
+template <int NT, int VAR>
+__device__ __noinline__ void y_level_exact(YLevel<NT> *L) { y_level<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
 __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const SwebyArgs<NT> a, const int nxt)
@@ -271,8 +409,6 @@ __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const 
     const int i = min(i_raw, g.ni);
     const int js = jc * a.kc + 1;
     const int je = min(js + a.kc - 1, g.nj);
-    const double dtime = a.dtime;
-    const Rcp rdt = make_rcp(dtime);
     const size_t nxd = (size_t)g.nxd, tp = (size_t)g.tpitch;
     const size_t wofs = (size_t)g.slab;    // w3(k) = d3(k) + slab ; w3(k-1) = d3(k)
     const bool has_km1 = (k > 1);
@@ -307,20 +443,22 @@ __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const 
     cp_async_commit();
 
     // state at face jf = js-1
-    unsigned nb = a.nib[q];
-    double t0[NT], t1[NT], Rm1[NT], R0[NT], fprev[NT];
+    YLevel<NT> L;
+    L.dtime = a.dtime; L.sl = a.sl;
+    L.nb = a.nib[q];
 #pragma unroll
     for (int n = 0; n < NT; n++) {
         const double tmm = a.tm_in[n][tq - tp];
-        t0[n] = a.tm_in[n][tq];
-        t1[n] = a.tm_in[n][tq + tp];
-        Rm1[n] = (t0[n] - tmm) * nib_and(nb, 3u);     // ((tm(j)-tm(j-1))*m(j))*m(j-1)
-        R0[n] = (t1[n] - t0[n]) * nib_and(nb, 6u);    // ((tm(j+1)-tm(j))*m(j+1))*m(j)
-        fprev[n] = 0.0;
+        L.t0[n] = a.tm_in[n][tq];
+        L.t1[n] = a.tm_in[n][tq + tp];
+        L.Rm1[n] = (L.t0[n] - tmm) * nib_and(L.nb, 3u);     // ((tm(j)-tm(j-1))*m(j))*m(j-1)
+        L.R0[n] = (L.t1[n] - L.t0[n]) * nib_and(L.nb, 6u);  // ((tm(j+1)-tm(j))*m(j+1))*m(j)
+        L.fprev[n] = 0.0;
     }
-    double rho0 = a.rho[q];
+    L.rho0 = a.rho[q];
 
     int st = 0;
+#pragma unroll 3
     for (int jf = js - 1; jf <= je; jf++, q += nxd, c2 += nxd, tq += tp, st ^= 1) {
         __syncwarp();
         unsigned nb_n = 0;
@@ -332,53 +470,40 @@ __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const 
         cp_async_wait<1>();
         __syncwarp();
         double(*S)[YROW] = sm[st][wy];
-        const double vv = S[F_V][lane + 1];
-        const double rho1 = S[F_RHO][lane + 1];
-        const double mf = S[F_DXTN][lane + 1] * vv;
-        const FaceCoef c = make_coef(mf, fabs(div_rcp((vv * dtime) * 2.0, make_rcp((rho0 + rho1) * S[F_DYTN][lane + 1]))), nib_and(nb, 6u));
-        const double mm23 = nib_and(nb, 12u), m0 = nib_and(nb, 2u);
-        const bool live = (jf >= js);
-        double wdiv = 0.0, datr = 0.0;
-        Rcp rr;
-        rr.b = 1.0; rr.y = 1.0;
-        if (live) {   // T*( (w(k)-wkm1) + datr*(dyte(i-1)*u(i-1) - dyte(i)*u(i)) )  (OTA:4402-4406)
-            datr = S[F_DATR][lane + 1];
-            const double wk = S[F_WK][lane + 1];
-            const double wkm1 = has_km1 ? S[F_WM][lane + 1] : 0.0;
-            wdiv = (wk - wkm1) + (datr * ((S[F_DYTE][lane] * S[F_U][lane]) - (S[F_DYTE][lane + 1] * S[F_U][lane + 1])));
-            rr = make_rcp(rho0);
+        L.live = (jf >= js);
+        L.vv = S[F_V][lane + 1];
+        L.rho1 = S[F_RHO][lane + 1];
+        L.dxtn = S[F_DXTN][lane + 1];
+        L.dytn = S[F_DYTN][lane + 1];
+        L.datr = S[F_DATR][lane + 1];
+        L.wk = S[F_WK][lane + 1];
+        L.wkm1 = has_km1 ? S[F_WM][lane + 1] : 0.0;
+        L.dyte_w = S[F_DYTE][lane]; L.u_w = S[F_U][lane];
+        L.dyte_c = S[F_DYTE][lane + 1]; L.u_c = S[F_U][lane + 1];
+#pragma unroll
+        for (int n = 0; n < NT; n++) { L.t2[n] = S[n][lane + 1]; L.Tc[n] = S[F_T + n][lane + 1]; }
+        if (y_level<NT, VAR, false>(L)) {
+            YLevel<NT> X = L;
+            y_level_exact<NT, VAR>(&X);
+#pragma unroll
+            for (int n = 0; n < NT; n++) { L.f[n] = X.f[n]; L.Rp1[n] = X.Rp1[n]; L.adv[n] = X.adv[n]; L.wy[n] = X.wy[n]; }
         }
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-            const double t2 = S[n][lane + 1];
-            const double Rp1 = (t2 - t1[n]) * mm23;   // ((tm(j+2)-tm(j+1))*m(j+2))*m(j+1)
-            const double f = sweby_flux<VAR>(c, Rp1, R0[n], Rm1[n], t0[n], t1[n], a.sl);
-            if (DIAG && ok && a.flux[n]) a.flux[n][q] = f;
-            if (live) {
-                const double Tc = S[F_T + n][lane + 1];
-                double t;
-                if (VAR == VAR_ALL) {  // OTA:4401-4413
-                    const double wy_ = ((m0 * datr) * (fprev[n] - f)) + (Tc * wdiv);
-                    t = t0[n] + div_rcp(wy_ * dtime, rr);
-                    if (DIAG && ok && a.dadv[n]) a.dadv[n][q] = wy_;
-                } else {               // OTA:4025-4040
-                    t = t0[n] + (div_rcp((dtime * m0) * datr, rr) * (fprev[n] - f));
-                    t = t + (div_rcp(dtime * Tc, rr) * wdiv);
-                }
-                const double adv = div_rcp(rho0 * (t - Tc), rdt) * m0;
-                if (ok) {
-                    a.adv[n][q] = adv;
-                    if (a.accumulate) a.th[n][q] = S[F_TH + n][lane + 1] + adv;
-                }
+            if (DIAG && ok && a.flux[n]) a.flux[n][q] = L.f[n];
+            if (L.live && ok) {
+                a.adv[n][q] = L.adv[n];
+                if (a.accumulate) a.th[n][q] = S[F_TH + n][lane + 1] + L.adv[n];
+                if (DIAG && VAR == VAR_ALL && a.dadv[n]) a.dadv[n][q] = L.wy[n];
             }
-            fprev[n] = f;
-            Rm1[n] = R0[n];
-            R0[n] = Rp1;
-            t0[n] = t1[n];
-            t1[n] = t2;
+            L.fprev[n] = L.f[n];
+            L.Rm1[n] = L.R0[n];
+            L.R0[n] = L.Rp1[n];
+            L.t0[n] = L.t1[n];
+            L.t1[n] = L.t2[n];
         }
-        rho0 = rho1;
-        nb = nb_n;
+        L.rho0 = L.rho1;
+        L.nb = nb_n;
     }
 }
 

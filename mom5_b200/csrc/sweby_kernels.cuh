@@ -7,15 +7,14 @@
 // Thread mapping (lanes always run along i, the contiguous index, so every global access is coalesced):
 //   z sweep: one thread per (i,j) column marching down k; the k-carried quantities of the reference
 //            (ftp, wkm1) and the three limiter differences R(k-1), R(k), R(k+1) live in registers, so every
-//            z-face flux and every difference is computed exactly once.  The next level's operands are loaded
-//            into registers one iteration ahead (software pipelining).
+//            z-face flux and every difference is computed exactly once.
 //   x sweep: one thread per (i,j) east face, looping over k with the 2-D metrics in registers.  A warp owns
 //            32 consecutive faces = 31 cells; the west-face flux and mass flux come from the neighbouring lane by
 //            warp shuffle and tm(i-1..i+2) from the warp's staged row, so warps are independent (no block barrier).
 //   y sweep: one thread per (i,k) marching north over a chunk of j with a rolling register window
 //            (tm(j-1..j+2), R(j-1..j+1), flux(j-1)); blocks are ordered k-fastest so that the 2-D metrics and
 //            w(k-1) of concurrently resident blocks hit in L2.
-// x and y stage the next iteration's operands global -> shared with per-thread cp.async (LDGSTS) one iteration
+// All three stage the next iteration's operands global -> shared with per-thread cp.async (LDGSTS) one iteration
 // ahead: no register cost, no block barrier (warps stage and consume their own rows; __syncwarp only).
 // All NT tracers of a group are advanced by the same thread so the tracer-independent face coefficients
 // (cfl, d0, d1, (1-cfl)/(1e-30+cfl), mf+-|mf|, mask products, reciprocals of rho_dzt and dtime) are computed once.
@@ -77,7 +76,7 @@ template <int NT, int VAR, bool EXACT>
 __device__ __forceinline__ unsigned z_level(ZLevel<NT> &L)
 {
     unsigned bad = 0;
-    const Div<EXACT> rr(L.r, bad);
+    const Div<EXACT> rr = Div<EXACT>::make(L.r, bad);
     const FaceCoef c = make_coef<EXACT>(L.dat * L.wk, fabs(rr(L.wk * L.dtime, bad)), nib_and(L.nb, 6u), bad);
     const double mm12 = nib_and(L.nb, 12u);           // m(kp1)*m(kp2)
     const double dtr = (VAR == VAR_ONE) ? rr(L.dtime, bad) : 0.0;
@@ -102,9 +101,12 @@ __device__ __noinline__ void z_level_exact(ZLevel<NT> *L) { z_level<NT, VAR, tru
 template <int NT, int VAR, bool DIAG>
 __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArgs<NT> a)
 {
-    const int i = blockIdx.x * ZBX + threadIdx.x + 1;
+    constexpr int NF = NT + 2;                           // T(kp2)[NT], w, rho of the next level
+    __shared__ double sm[2][NF][ZBX];
+    const int tx = threadIdx.x;
+    const int i = blockIdx.x * ZBX + tx + 1;
     const int j = blockIdx.y + 1;
-    if (i > g.ni) return;
+    if (i > g.ni) return;                                // staging is per thread: no collective operation follows
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
     const int k0 = ks > 1 ? ks - 1 : 1;  // first face evaluated (warm-up face when the chunk starts below the surface)
@@ -116,6 +118,15 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
     size_t q2 = qd + slab * (size_t)(min(k0 + 2, g.nk) - k0);     // data-domain offset of level min(k+2, nk)
     const size_t qkm = (k0 > 1) ? qd - slab : qd, qkp = (k0 < g.nk) ? qd + slab : qd;
 
+    auto stage = [&](int st, size_t qd_, size_t q2_) {   // operands of the level whose offsets are (qd_, q2_)
+#pragma unroll
+        for (int n = 0; n < NT; n++) cp_async8(&sm[st][n][tx], a.T[n] + q2_);
+        cp_async8(&sm[st][NT][tx], a.w + qd_ + slab);             // w3(k) = d3(k) + slab
+        cp_async8(&sm[st][NT + 1][tx], a.rho + qd_);
+    };
+    stage(0, qd, q2);
+    cp_async_commit();
+
     ZLevel<NT> L;
     L.dat = a.dat[c2]; L.datr = a.datr[c2]; L.dtime = a.dtime; L.sl = a.sl;
     L.nb = a.nib[qd];
@@ -124,32 +135,29 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
         const double Tkm = a.T[n][qkm];
         L.Tk[n] = a.T[n][qd];
         L.Tp1[n] = a.T[n][qkp];
-        L.Tp2[n] = a.T[n][q2];
         L.Rm1[n] = (Tkm - L.Tk[n]) * nib_and(L.nb, 3u);      // ((T(km1)-T(k))*m(km1))*m(k); +0 at k = 1 (km1 clamps)
         L.R0[n] = (L.Tk[n] - L.Tp1[n]) * nib_and(L.nb, 6u);  // ((T(k)-T(kp1))*m(k))*m(kp1)
         L.ftp[n] = 0.0;
     }
     L.wkm1 = 0.0;
-    L.wk = a.w[qd + slab];                               // w3(k) = d3(k) + slab
-    L.r = a.rho[qd];
 
+    int st = 0;
 #pragma unroll 3
-    for (int k = k0; k <= ke; k++) {
-        // ---- software pipeline: operands of level k+1 ----
-        const bool more = (k < ke);
+    for (int k = k0; k <= ke; k++, st ^= 1) {
+        // ---- stage the operands of level k+1 (each thread reads back only what it staged itself) ----
         const size_t qd_n = qd + slab;
         const size_t q2_n = (k + 3 <= g.nk) ? q2 + slab : q2;
         unsigned nb_n = 0;
-        double wk_n = 0.0, r_n = 1.0, Tp2_n[NT];
-#pragma unroll
-        for (int n = 0; n < NT; n++) Tp2_n[n] = 0.0;
-        if (more) {
+        if (k < ke) {
+            stage(st ^ 1, qd_n, q2_n);
             nb_n = a.nib[qd_n];
-            wk_n = a.w[qd_n + slab];
-            r_n = a.rho[qd_n];
-#pragma unroll
-            for (int n = 0; n < NT; n++) Tp2_n[n] = a.T[n][q2_n];
         }
+        cp_async_commit();
+        cp_async_wait<1>();
+#pragma unroll
+        for (int n = 0; n < NT; n++) L.Tp2[n] = sm[st][n][tx];
+        L.wk = sm[st][NT][tx];
+        L.r = sm[st][NT + 1][tx];
         // ---- level k ----
         if (z_level<NT, VAR, false>(L)) {
             ZLevel<NT> X = L;
@@ -170,11 +178,8 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
             L.R0[n] = L.Rp1[n];
             L.Tk[n] = L.Tp1[n];
             L.Tp1[n] = L.Tp2[n];
-            L.Tp2[n] = Tp2_n[n];
         }
         L.wkm1 = L.wk;
-        L.wk = wk_n;
-        L.r = r_n;
         L.nb = nb_n;
         qd = qd_n;
         q2 = q2_n;
@@ -200,7 +205,7 @@ __device__ __forceinline__ unsigned x_face(XFace<NT> &L)
 {
     unsigned bad = 0;
     L.mf = L.dyte * L.uu;
-    const FaceCoef c = make_coef<EXACT>(L.mf, fabs(Div<EXACT>((L.rho_i + L.rho_e) * L.dxte, bad)((L.uu * L.dtime) * 2.0, bad)),
+    const FaceCoef c = make_coef<EXACT>(L.mf, fabs(Div<EXACT>::make((L.rho_i + L.rho_e) * L.dxte, bad)((L.uu * L.dtime) * 2.0, bad)),
                                         nib_and(L.nb, 6u), bad);
     const double mm01 = nib_and(L.nb, 3u), mm23 = nib_and(L.nb, 12u);
 #pragma unroll
@@ -225,7 +230,7 @@ template <int NT, int VAR, bool EXACT>
 __device__ __forceinline__ unsigned x_cell(XCell<NT> &L)
 {
     unsigned bad = 0;
-    const Div<EXACT> rr(L.rho_i, bad);
+    const Div<EXACT> rr = Div<EXACT>::make(L.rho_i, bad);
     const double coef = (VAR == VAR_ONE) ? rr((L.dtime * L.m_i) * L.datr, bad) : 0.0;
 #pragma unroll
     for (int n = 0; n < NT; n++) {
@@ -358,7 +363,7 @@ __device__ __forceinline__ unsigned y_level(YLevel<NT> &L)
 {
     unsigned bad = 0;
     const double mf = L.dxtn * L.vv;
-    const FaceCoef c = make_coef<EXACT>(mf, fabs(Div<EXACT>((L.rho0 + L.rho1) * L.dytn, bad)((L.vv * L.dtime) * 2.0, bad)),
+    const FaceCoef c = make_coef<EXACT>(mf, fabs(Div<EXACT>::make((L.rho0 + L.rho1) * L.dytn, bad)((L.vv * L.dtime) * 2.0, bad)),
                                         nib_and(L.nb, 6u), bad);
     const double mm23 = nib_and(L.nb, 12u), m0 = nib_and(L.nb, 2u);
 #pragma unroll
@@ -369,7 +374,7 @@ __device__ __forceinline__ unsigned y_level(YLevel<NT> &L)
     if (L.live) {
         // T*( (w(k)-wkm1) + datr*(dyte(i-1)*u(i-1) - dyte(i)*u(i)) )  (OTA:4402-4406)
         const double wdiv = (L.wk - L.wkm1) + (L.datr * ((L.dyte_w * L.u_w) - (L.dyte_c * L.u_c)));
-        const Div<EXACT> rr(L.rho0, bad), rdt(L.dtime, bad);
+        const Div<EXACT> rr = Div<EXACT>::make(L.rho0, bad), rdt = Div<EXACT>::make(L.dtime, bad);
         const double c1 = (VAR == VAR_ONE) ? rr((L.dtime * m0) * L.datr, bad) : 0.0;
 #pragma unroll
         for (int n = 0; n < NT; n++) {

@@ -121,6 +121,33 @@ def test_sweby_all_vs_oracle(case, over):
             assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {nm}[{n}]")
 
 
+@pytest.mark.parametrize("case", ["mini_tripolar", "mini_walls"])
+def test_tiny_and_underflowing_tracers_take_the_exact_division_path(case):
+    """Tracer values near the bottom of the binary64 range (a dye patch whose Gaussian tail underflows, a field scaled
+    by 2^-1000) make the shared-reciprocal division guards fire; the out-of-line exact path must then reproduce the
+    oracle bit for bit (subnormal quotients, tiny numerators)."""
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    g = make_case(case)
+    b = g.block()
+    nk, ny, nx = b.T[0].shape
+    jj, ii = torch.meshgrid(torch.arange(ny, dtype=torch.float64), torch.arange(nx, dtype=torch.float64), indexing="ij")
+    b.T[0] = (b.T[0] * 2.0 ** -1000).contiguous()                                   # all differences ~1e-301 .. subnormal
+    gauss = torch.exp(-(((ii - nx / 2) / 1.1) ** 2 + ((jj - ny / 2) / 1.3) ** 2) * 3.0)  # tail underflows to 0 through subnormals
+    b.T[1] = (gauss[None] * torch.ones(nk, 1, 1, dtype=torch.float64)).contiguous()
+    assert (b.T[1] == 0).any() and ((b.T[1] > 0) & (b.T[1] < 1e-300)).any()
+    dec = g.s.decomposition(1, 1)
+    o = Oracle(dec, [b])
+    th = [[t.numpy().copy() for t in b.th_tendency]]
+    ref = o.sweby_all([[t.numpy() for t in b.T]], th, g.s.dtime, diag=True)
+    r = _run_sweby_all_dev(b, diag=True)
+    for n in range(len(b.T)):
+        assert_bit_equal(r["th"][n], th[0][n], f"{case} th[{n}]")
+        assert_bit_equal(r["adv"][n], ref["adv"][0][n], f"{case} adv[{n}]")
+        for nm in ("flux_x", "flux_y", "flux_z", "adv_x", "adv_y", "adv_z"):
+            assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {nm}[{n}]")
+
+
 def test_invalid_scheme_is_an_error():
     from mom5_b200._lib import Mom5AdvError
     from mom5_b200.api import TracerAdvect

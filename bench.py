@@ -216,6 +216,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     comm = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         comm = Communicator.create_from_torch_distributed()
 

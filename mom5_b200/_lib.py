@@ -51,16 +51,22 @@ DEBUG_SYMBOLS = {
 }
 
 _lib = None
+FMA_LIB_PATH = os.path.join(_HERE, "libmom5adv_fma.so")
 
 
 def load() -> C.CDLL:
-    """dlopen the in-tree library.  Raises if it has not been built (python -m mom5_b200.build)."""
+    """dlopen the in-tree library.  Raises if it has not been built (python -m mom5_b200.build).
+    MOM5ADV_FMA=1 in the environment selects, for the whole process, the FMA-contracted build
+    (python -m mom5_b200.build --fma): not bit-exact, <= 1e-12 relative on the updated tracer.  The two builds
+    are never loaded into one process (each carries its own static CUDA runtime and the same kernel symbols)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m mom5_b200.build` "
+        fma = os.environ.get("MOM5ADV_FMA", "0") == "1"
+        path = FMA_LIB_PATH if fma else LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -m mom5_b200.build{' --fma' if fma else ''}` "
                                "(there is no CPU fallback for the advection path)")
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         for name, (res, args) in {**SYMBOLS, **DEBUG_SYMBOLS}.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

@@ -4,6 +4,7 @@
 #include <nccl.h>   // types only: the library is dlopen'ed on first use (see nccl_api below)
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -98,6 +99,12 @@ struct mom5adv_ctx {
     std::vector<double *> hm;          // generic pool of data-domain device arrays
     double *hm_w = 0;
     cudaStream_t stream = 0;           // library-owned stream for the host-pointer entry points
+    cudaStream_t s_up = 0, s_down = 0; // copy streams of the pipelined host-pointer path
+    cudaStream_t s_comm = 0;           // halo exchange stream (overlapped with interior tiles)
+    cudaEvent_t ev_sync[4];
+    int overlap = 1;                   // MOM5ADV_OVERLAP=0 disables the comm/compute overlap
+    int y_rows = 32;
+    std::vector<cudaEvent_t> ev_up, ev_done;
     cudaEvent_t ev[6];
     bool ev_valid = false;
     int64_t launches = 0;
@@ -505,6 +512,16 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
         CUDA_TRY(cudaMemset(h->tmB[n], 0, nh2(h) * sizeof(double)));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sync[e], cudaEventDisableTiming));
+    if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    h->ev_up.resize(ntracers_max); h->ev_done.resize(ntracers_max);
+    for (int n = 0; n < ntracers_max; n++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_up[n], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[n], cudaEventDisableTiming));
+    }
     for (int e = 0; e < 6; e++) CUDA_TRY(cudaEventCreate(&h->ev[e]));
     DomInfo D{h->ni_g, h->nj_g, h->px, h->py, h->cyclic_x, h->cyclic_y, h->tripolar, &h->ibeg, &h->iend, &h->jbeg, &h->jend};
     for (int f = 1; f <= 3; f++) build_plan(D, h->rank, f, 2, h->plan[f]);
@@ -544,6 +561,12 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
     free_quickw(h->qw);
     for (int e = 0; e < 6; e++) cudaEventDestroy(h->ev[e]);
     cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->s_up);
+    cudaStreamDestroy(h->s_comm);
+    for (int e = 0; e < 4; e++) cudaEventDestroy(h->ev_sync[e]);
+    cudaStreamDestroy(h->s_down);
+    for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -560,28 +583,34 @@ static int pick_kchunk(const Geom &g, int per_level_threads)
     return (g.nk + nch - 1) / nch;
 }
 
+// part: 0 = whole sweep, 1 = interior tiles only (they read no halo), 2 = the two edge tiles (after the halo update)
 template <int NT, int VAR, bool DIAG>
-static void launch_group(mom5adv_ctx *h, int phase, const SwebyArgs<NT> &a, cudaStream_t st)
+static void launch_group(mom5adv_ctx *h, int phase, int part, const SwebyArgs<NT> &a, cudaStream_t st)
 {
     const Geom &g = h->g;
     SwebyArgs<NT> b = a;
+    b.tile_first = 0; b.tile_step = 1;
     if (phase == 0) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
         dim3 grid((g.ni + ZBX - 1) / ZBX, g.nj, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, ZBX, 0, st, g, b);
     } else if (phase == 1) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
-        dim3 grid((g.ni + 30) / 31, (g.nj + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
+        const int nxt = (g.ni + 30) / 31;
+        int ntile = nxt;
+        if (part == 1) { b.tile_first = 1; ntile = nxt - 2; }
+        if (part == 2) { b.tile_step = nxt - 1; ntile = 2; }
+        dim3 grid(ntile, (g.nj + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(32, XWARPS), 0, st, g, b);
     } else {
         const int YBX = 32 * YWARPS;
         const int nxt = (g.ni + YBX - 1) / YBX;
-        const long long per_chunk = (long long)nxt * YBX * g.nk;
-        int rows = 32;
-        while (rows > 8 && per_chunk * ((g.nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
-        b.kc = rows;
-        const int njc = (g.nj + rows - 1) / rows;
-        LAUNCH(h, (k_sweby_y<NT, VAR, DIAG>), (unsigned)(g.nk * nxt * njc), YBX, 0, st, g, b, nxt);
+        b.kc = h->y_rows;
+        const int njc = (g.nj + b.kc - 1) / b.kc;
+        int nch = njc;
+        if (part == 1) { b.tile_first = 1; nch = njc - 2; }
+        if (part == 2) { b.tile_step = njc - 1; nch = 2; }
+        LAUNCH(h, (k_sweby_y<NT, VAR, DIAG>), (unsigned)(g.nk * nxt * nch), YBX, 0, st, g, b, nxt);
     }
 }
 
@@ -596,7 +625,7 @@ struct SwebyCall {
 };
 
 template <int NT>
-static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cudaStream_t st)
+static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, int part, cudaStream_t st)
 {
     SwebyArgs<NT> a{};
     bool diag = false;
@@ -616,15 +645,15 @@ static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cud
     a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
     a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;
     if (c.var == VAR_ALL) {
-        if (diag) launch_group<NT, VAR_ALL, true>(h, phase, a, st);
-        else launch_group<NT, VAR_ALL, false>(h, phase, a, st);
+        if (diag) launch_group<NT, VAR_ALL, true>(h, phase, part, a, st);
+        else launch_group<NT, VAR_ALL, false>(h, phase, part, a, st);
     } else {
-        if (diag) launch_group<NT, VAR_ONE, true>(h, phase, a, st);
-        else launch_group<NT, VAR_ONE, false>(h, phase, a, st);
+        if (diag) launch_group<NT, VAR_ONE, true>(h, phase, part, a, st);
+        else launch_group<NT, VAR_ONE, false>(h, phase, part, a, st);
     }
 }
 
-static void run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, cudaStream_t st)
+static void run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, int part, cudaStream_t st)
 {
     for (int n0 = 0; n0 < c.ntr;) {
         const int left = c.ntr - n0;
@@ -632,10 +661,10 @@ static void run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, cudaStr
         const int ngroups = (left + MAXNT - 1) / MAXNT;
         const int nt = (left + ngroups - 1) / ngroups;
         switch (nt) {
-        case 1: run_phase<1>(h, c, n0, phase, st); break;
-        case 2: run_phase<2>(h, c, n0, phase, st); break;
-        case 3: run_phase<3>(h, c, n0, phase, st); break;
-        default: run_phase<4>(h, c, n0, phase, st); break;
+        case 1: run_phase<1>(h, c, n0, phase, part, st); break;
+        case 2: run_phase<2>(h, c, n0, phase, part, st); break;
+        case 3: run_phase<3>(h, c, n0, phase, part, st); break;
+        default: run_phase<4>(h, c, n0, phase, part, st); break;
         }
         n0 += nt;
     }
@@ -651,21 +680,66 @@ static int zero_rings(mom5adv_ctx *h, double *const *arrs, int n, cudaStream_t s
     return 0;
 }
 
+static bool plan_has_remote(const mom5adv_ctx *h, int flags)
+{
+    for (const Msg &m : h->plan[flags & 3].recvs) if (m.peer != h->rank) return true;
+    for (const Msg &m : h->plan[flags & 3].sends) if (m.peer != h->rank) return true;
+    return false;
+}
+
 static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
     if (c.ntr < 1 || c.ntr > h->ntr_max) { set_error("sweby: ntr=%d outside 1..%d", c.ntr, h->ntr_max); return MOM5ADV_EINVAL; }
     int rc;
+    const Geom &g = h->g;
+    // y-sweep chunking (rows per j-chunk): >= ~4 waves of threads, at most 32 rows
+    {
+        const int YBX = 32 * YWARPS;
+        const long long per_chunk = (long long)((g.ni + YBX - 1) / YBX) * YBX * g.nk;
+        int rows = 32;
+        while (rows > 8 && per_chunk * ((g.nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
+        h->y_rows = rows;
+    }
+    const int nxt = (g.ni + 30) / 31, njc = (g.nj + h->y_rows - 1) / h->y_rows;
+    // Overlap the NCCL strip exchange with the interior tiles of the sweep that consumes it (the reference's only
+    // overlap is tracer n's exchange with tracer n+1's compute, OTA:4214-4216): the exchange runs on the library's comm
+    // stream while the x (y) sweep works on the tiles (j-chunks) that read no halo; the two edge tiles follow.
+    const bool ovx = h->overlap && plan_has_remote(h, 1) && nxt >= 4;
+    const bool ovy = h->overlap && plan_has_remote(h, 2) && njc >= 4;
+    cudaStream_t sc = h->s_comm;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     zero_rings(h, c.adv, c.ntr, st);
-    run_phase_all(h, c, 0, st);
+    run_phase_all(h, c, 0, 0, st);
     CUDA_TRY(cudaEventRecord(h->ev[1], st));
-    if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev[2], st));
-    run_phase_all(h, c, 1, st);
+    if (ovx) {
+        CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[0], 0));
+        if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
+        CUDA_TRY(cudaEventRecord(h->ev[2], st));
+        run_phase_all(h, c, 1, 1, st);
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
+        run_phase_all(h, c, 1, 2, st);
+    } else {
+        if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[2], st));
+        run_phase_all(h, c, 1, 0, st);
+    }
     CUDA_TRY(cudaEventRecord(h->ev[3], st));
-    if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev[4], st));
-    run_phase_all(h, c, 2, st);
+    if (ovy) {
+        CUDA_TRY(cudaEventRecord(h->ev_sync[2], st));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[2], 0));
+        if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, sc))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[3], sc));
+        CUDA_TRY(cudaEventRecord(h->ev[4], st));
+        run_phase_all(h, c, 2, 1, st);
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[3], 0));
+        run_phase_all(h, c, 2, 2, st);
+    } else {
+        if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[4], st));
+        run_phase_all(h, c, 2, 0, st);
+    }
     CUDA_TRY(cudaEventRecord(h->ev[5], st));
     h->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
@@ -735,6 +809,42 @@ extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const 
                     H2D(dd[q][n], hd[q][n], N);   // points outside the loop ranges keep the caller's values
                 }
         }
+    bool any_diag = false;
+    for (int q = 0; q < 6; q++) any_diag |= (hd[q] != nullptr);
+    if (!any_diag && ntr > 1) {
+        // Pipelined over tracers: the copy engines run in both directions while the SMs work on another tracer.
+        //   up stream  : u, v, w, rho, then (T_n, th_n) for n = 0, 1, ...
+        //   compute    : tracer n as soon as its inputs have landed (results do not depend on the grouping of tracers)
+        //   down stream: th_n, adv_n as soon as tracer n is done -- overlapping the upload of tracer n+1
+        cudaStream_t up = h->s_up, down = h->s_down;
+        {
+            cudaStream_t st = up;
+            H2D(du, u, N); H2D(dv, v, N); H2D(dr, rho, N);
+            H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1));
+        }
+        for (int n = 0; n < ntr; n++) {
+            {
+                cudaStream_t st = up;
+                H2D(dT[n], T[n], N); H2D(dth[n], th[n], N);
+            }
+            CUDA_TRY(cudaEventRecord(h->ev_up[n], up));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_up[n], 0));
+            const double *Tn[1] = {dT[n]};
+            double *thn[1] = {dth[n]}, *advn[1] = {dadv[n]};
+            SwebyCall c1{1, VAR_ALL, dtime, 1.0, Tn, thn, advn, du, dv, dw, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1};
+            if ((rc = sweby_dev(h, c1, st))) return rc;
+            CUDA_TRY(cudaEventRecord(h->ev_done[n], st));
+            CUDA_TRY(cudaStreamWaitEvent(down, h->ev_done[n], 0));
+            {
+                cudaStream_t st = down;
+                D2H(th[n], dth[n], N);
+                if (adv && adv[n]) D2H(adv[n], dadv[n], N);
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(down));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return 0;
+    }
     H2D(du, u, N); H2D(dv, v, N); H2D(dr, rho, N);
     H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1));
     for (int n = 0; n < ntr; n++) { H2D(dT[n], T[n], N); H2D(dth[n], th[n], N); }
@@ -748,6 +858,76 @@ extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const 
             if (hd[q] && hd[q][n]) D2H(hd[q][n], dd[q][n], N);
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fold-line fix of the quicker fluxes (OTA:2640), possibly across ranks
+// ------------------------------------------------------------------------------------------------
+static int fold_line_fix(mom5adv_ctx *h, double *fy, cudaStream_t st)
+{
+    if (h->iy != h->py - 1) return 0;                      // only the top row of ranks touches the fold
+    const int middle = (1 + h->ni_g) / 2 + 1;
+    const int nk = h->g.nk;
+    // enumerate, for every top-row rank r, the destination segments (global i >= middle) split by the owner of the mirror image
+    struct Seg { int dst_rank, src_rank, dst_i1g, src_i0g, w; };
+    std::vector<Seg> segs;
+    for (int bx = 0; bx < h->px; bx++) {
+        int a = std::max(h->ibeg[bx], middle), b = h->iend[bx];
+        while (a <= b) {
+            // destination run [a, e] whose mirror [ni_g+1-e, ni_g+1-a] lies in ONE source block
+            const int sx = find_div(h->ibeg, h->iend, h->ni_g + 1 - a);
+            const int e = std::min(b, h->ni_g + 1 - h->ibeg[sx]);
+            segs.push_back({bx + h->px * h->iy, sx + h->px * h->iy, e, h->ni_g + 1 - e, e - a + 1});
+            a = e + 1;
+        }
+    }
+    FoldArgs L{}, S{}, R{};
+    std::vector<int> speer, rpeer;
+    L.fy = S.fy = R.fy = fy;
+    auto add = [&](FoldArgs &A, int src_i0, int dst_i1, int w) {
+        if (A.nseg >= FOLD_MAXSEG) return false;
+        A.s[A.nseg] = FoldSeg{src_i0, dst_i1, w, A.start[A.nseg]};
+        A.start[A.nseg + 1] = A.start[A.nseg] + (long long)w * nk;
+        A.nseg++;
+        return true;
+    };
+    const int my_i0g = h->ibeg[h->ix];
+    bool ok = true;
+    // deterministic order on both sides: by (dst_rank, src_rank, position)
+    for (const Seg &sg : segs) {
+        if (sg.dst_rank == h->rank && sg.src_rank == h->rank) ok &= add(L, sg.src_i0g - my_i0g + 1, sg.dst_i1g - my_i0g + 1, sg.w);
+        else if (sg.src_rank == h->rank) { ok &= add(S, sg.src_i0g - my_i0g + 1, 0, sg.w); speer.push_back(sg.dst_rank); }
+        else if (sg.dst_rank == h->rank) { ok &= add(R, 0, sg.dst_i1g - my_i0g + 1, sg.w); rpeer.push_back(sg.src_rank); }
+    }
+    if (!ok) { set_error("fold-line fix: too many segments"); return MOM5ADV_EINVAL; }
+    auto nblk = [](long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 8); };
+    if (L.nseg) LAUNCH(h, k_fold_line<0>, nblk(L.start[L.nseg]), 256, 0, st, h->g, L);
+    if (S.nseg || R.nseg) {
+        if (!h->comm) { set_error("fold-line fix needs a communicator"); return MOM5ADV_EINVAL; }
+        const size_t need = (size_t)std::max(S.start[S.nseg], R.start[R.nseg]);
+        if (need > h->bufcap) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (h->sendbuf) cudaFree(h->sendbuf);
+            if (h->recvbuf) cudaFree(h->recvbuf);
+            CUDA_TRY(cudaMalloc(&h->sendbuf, need * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->recvbuf, need * sizeof(double)));
+            h->bufcap = need;
+        }
+        S.buf = h->sendbuf;
+        R.buf = h->recvbuf;
+        if (S.nseg) LAUNCH(h, k_fold_line<1>, nblk(S.start[S.nseg]), 256, 0, st, h->g, S);
+        NCCL_NEED();
+        ncclComm_t comm = (ncclComm_t)h->comm->nccl;
+        NCCL_TRY(N->GroupStart());
+        for (int m = 0; m < S.nseg; m++)
+            NCCL_TRY(N->Send(h->sendbuf + S.start[m], (size_t)(S.start[m + 1] - S.start[m]), ncclDouble, speer[m], comm, st));
+        for (int m = 0; m < R.nseg; m++)
+            NCCL_TRY(N->Recv(h->recvbuf + R.start[m], (size_t)(R.start[m + 1] - R.start[m]), ncclDouble, rpeer[m], comm, st));
+        NCCL_TRY(N->GroupEnd());
+        if (R.nseg) LAUNCH(h, k_fold_line<2>, nblk(R.start[R.nseg]), 256, 0, st, h->g, R);
+    }
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -794,11 +974,11 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
         double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
         if (!tfx && (rc = mirror(h, 0, &tfx))) return rc;
         if (!tfy && (rc = mirror(h, 1, &tfy))) return rc;
-        rc = horz_quicker_dev(h->g, h->qw, h->tmask, h->mask, h->dyte, h->dxtn, h->datr, Tm1, Tt, h->tmA[0], tlimit,
-                              limit_with_upwind, u, v, th, wrk1, tfx, tfy, h->tripolar, h->ni_g, h->isc_g,
-                              h->jsc_g + g.nj - 1 == h->nj_g, st, &h->launches);
-        if (rc == -100) { set_error("quicker on a tripolar grid split in x needs the fold-line exchange (not implemented): use layout_x = 1"); return MOM5ADV_EUNSUP; }
-        return rc;
+        if ((rc = horz_quicker_flux_dev(h->g, h->qw, h->tmask, h->mask, h->dyte, h->dxtn, Tm1, Tt, h->tmA[0], tlimit,
+                                        limit_with_upwind, u, v, tfx, tfy, st, &h->launches))) { set_error("quicker flux kernel failed"); return MOM5ADV_ECUDA; }
+        if (h->tripolar && (rc = fold_line_fix(h, tfy, st))) return rc;
+        if ((rc = horz_div_dev(h->g, h->tmask, h->datr, tfx, tfy, th, wrk1, st, &h->launches))) { set_error("quicker divergence kernel failed"); return MOM5ADV_ECUDA; }
+        return 0;
     }
     default:
         set_error("mom5adv_horz_dev: chose invalid horz advection scheme %d", scheme);   // OTA:1983-1985

@@ -131,15 +131,38 @@ k_horz_flux(const Geom g, const QuickW q, const double *__restrict__ tmask, cons
     }
 }
 
-// OTA:2640 on a rank that spans the whole fold line: flux_y(i, nj) := -flux_y(ni+1-i, nj) for i >= ni/2+1
-// (MPPI/mpp_domains_define.inc:1617,2535-2549; see oracle/mom5adv_oracle.c:orc_fold_fix_flux)
-__global__ void k_fold_fix(const Geom g, double *__restrict__ fy)
+// OTA:2640  mpp_update_domains(flux_x, flux_y, Dom_flux, gridtype=CGRID_NE) on the folded north edge: the NORTH-position
+// component on the fold line is made antisymmetric, flux_y(i, nj) := -flux_y(ni_g+1-i, nj) for global i >= ni_g/2+1
+// (MPPI/mpp_domains_define.inc:1617,2535-2549; see oracle/mom5adv_oracle.c:orc_fold_fix_flux).
+// Segment descriptors are in LOCAL indices; element p of a segment is enumerated west -> east on the SOURCE side and
+// lands at (dst_i1 - p) on the destination side.
+struct FoldSeg {
+    int src_i0, dst_i1, w;
+    long long off;      // offset in the packed buffer
+};
+#define FOLD_MAXSEG 16
+struct FoldArgs {
+    int nseg;
+    long long start[FOLD_MAXSEG + 1];
+    FoldSeg s[FOLD_MAXSEG];
+    double *fy;
+    double *buf;
+};
+// mode 0: local (src and dst on this rank); 1: pack source row segments; 2: unpack (negated, reversed)
+template <int MODE>
+__global__ void k_fold_line(const Geom g, const FoldArgs a)
 {
-    const int middle = (1 + g.ni) / 2 + 1;
-    const int i = middle + blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y + 1;
-    if (i > g.ni) return;
-    fy[d3(g, i, g.nj, k)] = -fy[d3(g, g.ni + 1 - i, g.nj, k)];
+    const long long tot = a.start[a.nseg];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        int m = 0;
+        while (e >= a.start[m + 1]) m++;
+        const FoldSeg &sg = a.s[m];
+        const long long r = e - a.start[m];
+        const int p = (int)(r % sg.w), k = (int)(r / sg.w) + 1;
+        if (MODE == 0) a.fy[d3(g, sg.dst_i1 - p, g.nj, k)] = -a.fy[d3(g, sg.src_i0 + p, g.nj, k)];
+        if (MODE == 1) a.buf[sg.off + r] = a.fy[d3(g, sg.src_i0 + p, g.nj, k)];
+        if (MODE == 2) a.fy[d3(g, sg.dst_i1 - p, g.nj, k)] = -a.buf[sg.off + r];
+    }
 }
 
 // OTA:2642-2649 == 2282-2287, negated by the dispatcher (OTA:1936-1949), + th_tendency += wrk1 (OTA:1990-1996)
@@ -173,11 +196,10 @@ static int horz_upwind_dev(const Geom &g, const double *tmask, const double *dyt
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-static int horz_quicker_dev(const Geom &g, const QuickW &q, const double *tmask, const uint8_t *mq, const double *dyte,
-                            const double *dxtn, const double *datr, const double *Tm1, const double *Tt, const double *tq,
-                            const double *tlimit, int limit, const double *u, const double *v, double *th, double *wrk1,
-                            double *fx, double *fy, int tripolar, int ni_g, int isc_g, bool top_row, cudaStream_t st,
-                            int64_t *launches)
+static int horz_quicker_flux_dev(const Geom &g, const QuickW &q, const double *tmask, const uint8_t *mq, const double *dyte,
+                                 const double *dxtn, const double *Tm1, const double *Tt, const double *tq, const double *tlimit,
+                                 int limit, const double *u, const double *v, double *fx, double *fy, cudaStream_t st,
+                                 int64_t *launches)
 {
     // flux_x = flux_y = 0 (OTA:2568-2569)
     const size_t bytes = (size_t)g.slab * g.nk * sizeof(double);
@@ -185,14 +207,12 @@ static int horz_quicker_dev(const Geom &g, const QuickW &q, const double *tmask,
     dim3 gf((g.ni + 1 + 127) / 128, g.nj + 1, g.nk);
     k_horz_flux<true><<<gf, 128, 0, st>>>(g, q, tmask, mq, dyte, dxtn, Tm1, Tt, tq, tlimit, limit, u, v, fx, fy);
     *launches += 1;
-    if (tripolar && top_row) {
-        if (g.ni != ni_g || isc_g != 1) return -100;   // fold line split across ranks
-        const int n = g.ni - ((1 + g.ni) / 2 + 1) + 1;
-        if (n > 0) {
-            k_fold_fix<<<dim3((n + 127) / 128, g.nk), 128, 0, st>>>(g, fy);
-            *launches += 1;
-        }
-    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static int horz_div_dev(const Geom &g, const double *tmask, const double *datr, const double *fx, const double *fy, double *th,
+                        double *wrk1, cudaStream_t st, int64_t *launches)
+{
     dim3 gd((g.ni + 2 + 127) / 128, g.nj + 2, g.nk);
     k_horz_div<<<gd, 128, 0, st>>>(g, tmask, datr, fx, fy, th, wrk1);
     *launches += 1;

@@ -41,6 +41,7 @@ struct SwebyArgs {
     double dtime, sl;
     int kc;                     // z/x: levels per k-chunk;  y: rows per j-chunk
     int accumulate;             // y: th += adv
+    int tile_first, tile_step;  // x: x-tile = tile_first + blockIdx.x*tile_step; y: j-chunk likewise (interior / edge launches)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
     constexpr int NF = 2 * NT + 2;                       // tm[NT], T[NT], u, rho
     __shared__ double sm[2][XWARPS][NF][XROW];
     const int lane = threadIdx.x, wy = threadIdx.y;
-    const int iw = blockIdx.x * 31;                      // first east-face index of this warp
+    const int iw = (a.tile_first + (int)blockIdx.x * a.tile_step) * 31;   // first east-face index of this warp
     const int i = iw + lane;                             // east-face index 0..ni; lanes >= 1 also update cell i
     const int j = blockIdx.y * XWARPS + wy + 1;
     if (j > g.nj) return;                                // whole warp leaves together
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const 
     const int lin = blockIdx.x;
     const int k = lin % g.nk + 1;
     const int rest = lin / g.nk;
-    const int xt = rest % nxt, jc = rest / nxt;
+    const int xt = rest % nxt, jc = a.tile_first + (rest / nxt) * a.tile_step;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     const int i_raw = xt * (32 * YWARPS) + threadIdx.x + 1;
     if (i_raw - lane > g.ni) return;                     // the whole warp is outside: leave together

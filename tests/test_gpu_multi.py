@@ -45,16 +45,15 @@ def _worker(rank, world, port, case, over, px, py, outdir):
     out = [torch.empty_like(t) for t in T]
     u, v, w, rho = b.uhrho_et.cuda(), b.vhrho_nt.cuda(), b.wrho_bt.cuda(), b.rho_dzt.cuda()
     adv.advect_tracer_sweby_all(T, th, out, u, v, w, rho, g.s.dtime)
-    # single-tracer arms that exchange halos: mdfl_sweby (X then Y) and quicker (full update) when the fold is local
+    # single-tracer arms that exchange halos: mdfl_sweby (X then Y) and quicker (full update + fold line)
     th1 = b.th_tendency[0].cuda().clone()
     w1 = torch.empty_like(th1)
     adv.horz_advect_tracer(ADVECT_MDFL_SWEBY, T[0], th1, w1, u, v, g.s.dtime, wrho_bt=w, rho_dzt=rho)
     res = dict(ext=np.array([i0, i1, j0, j1]), scale=np.array(g.s.flow_scale), mdfl=w1.cpu().numpy())
-    if not (g.s.tripolar and px > 1):
-        th2 = b.th_tendency[0].cuda().clone()
-        w2 = torch.empty_like(th2)
-        adv.horz_advect_tracer(ADVECT_QUICKER, T[0], th2, w2, u, v, T_tau=b.T_tau[0].cuda(), tmask_limit=b.tmask_limit[0].cuda())
-        res["quicker"] = w2.cpu().numpy()
+    th2 = b.th_tendency[0].cuda().clone()   # quicker: full halo-2 update + (tripolar) the fold-line fix across ranks
+    w2 = torch.empty_like(th2)
+    adv.horz_advect_tracer(ADVECT_QUICKER, T[0], th2, w2, u, v, T_tau=b.T_tau[0].cuda(), tmask_limit=b.tmask_limit[0].cuda())
+    res["quicker"] = w2.cpu().numpy()
     torch.cuda.synchronize()
     for n in range(len(T)):
         res[f"th{n}"] = th[n].cpu().numpy()

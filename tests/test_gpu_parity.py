@@ -148,6 +148,71 @@ def test_tiny_and_underflowing_tracers_take_the_exact_division_path(case):
             assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {nm}[{n}]")
 
 
+def test_device_metrics_match_the_oracle():
+    """mpp_chksum (bit-pattern sum, mpp_chksum_int.h:20-38) and total_tracer (ocean_tracer_diag.F90:2405-2408)"""
+    from mom5_b200.api import TracerAdvect
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    g = make_case("mini_tripolar")
+    b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    adv = TracerAdvect(b, ntracers_max=1)
+    for n in range(len(b.T)):
+        t = _dev(b.T[n])
+        assert adv.chksum(t) == o.chksum([b.T[n].numpy()])
+        assert adv.chksum(t, masked=True) == o.chksum([b.T[n].numpy()], masked=True)
+        tot, ref = adv.total_tracer(_dev(b.rho_dzt), t), o.total_tracer([b.T[n].numpy()])
+        assert abs(tot - ref) <= 1e-12 * abs(ref)
+    adv.close()
+
+
+_FMA_CHILD = r"""
+import json, sys
+import numpy as np, torch
+from mom5_b200.api import TracerAdvect
+from mom5_b200.synthetic import make_case
+from oracle.oracle import Oracle
+worst = {}
+for case in ("mini_tripolar", "box1", "mini_walls"):
+    g = make_case(case); b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    th_ref = [[np.zeros_like(t.numpy()) for t in b.T]]
+    o.sweby_all([[t.numpy() for t in b.T]], th_ref, g.s.dtime)
+    adv = TracerAdvect(b, ntracers_max=len(b.T))
+    T = [t.cuda() for t in b.T]; th = [torch.zeros_like(t) for t in T]; out = [torch.empty_like(t) for t in T]
+    adv.advect_tracer_sweby_all(T, th, out, b.uhrho_et.cuda(), b.vhrho_nt.cuda(), b.wrho_bt.cuda(), b.rho_dzt.cuda(), g.s.dtime)
+    torch.cuda.synchronize()
+    rho = b.rho_dzt.numpy()
+    for n in range(len(T)):
+        Tn = b.T[n].numpy()
+        new_ref = (rho * Tn + g.s.dtime * th_ref[0][n]) / rho          # ocean_tracer.F90:2341-2350
+        new_fma = (rho * Tn + g.s.dtime * th[n].cpu().numpy()) / rho
+        worst[f"{case}.{n}"] = [float(np.abs(new_fma - new_ref).max() / np.abs(new_ref).max()),
+                                bool(np.array_equal(new_fma, new_ref))]
+    adv.close()
+print("RESULT " + json.dumps(worst))
+"""
+
+
+def test_fma_build_is_within_1e12_relative_on_the_updated_tracer():
+    """the north star's second correctness tier: with FMA contraction enabled (libmom5adv_fma.so, its own process) the
+    updated tracer T(taup1) = (rho_dzt*T + dtime*th_tendency)/rho_dzt stays within 1e-12 relative of the reference"""
+    import json
+    import os
+    import subprocess
+    import sys
+    TOL = 1e-12
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MOM5ADV_FMA="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", _FMA_CHILD], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert len(res) >= 7
+    for k, (rel, identical) in res.items():
+        assert rel <= TOL, (k, rel)
+    assert not all(identical for _, identical in res.values()), "the FMA build should differ in the last bits somewhere"
+
+
 def test_invalid_scheme_is_an_error():
     from mom5_b200._lib import Mom5AdvError
     from mom5_b200.api import TracerAdvect

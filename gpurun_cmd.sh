@@ -1,1 +1,1 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -5
+python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -3

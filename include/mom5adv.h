@@ -127,6 +127,15 @@ int mom5adv_vert_dev(mom5adv_handle h, int scheme,
                      const double *T_taum1, const double *T_tau, const double *tmask_limit,
                      const double *wrho_bt, double *th_tendency, double *wrk1_out, double *flux_z, void *stream);
 
+/* ---- consumer of the tendencies -------------------------------------------------
+ * T_taup1[n] := (rho_dzt_taum1*T_taum1[n] + dtime*th_tendency[n])*rho_dztr_taup1 on the compute domain
+ * (ocean_tracer.F90:2341-2350), followed by the halo-1 update of T_taup1[n] that update_ocean_model performs
+ * (mpp_update_domains(T_prog(n)%field(:,:,:,taup1), Dom%domain2d), ocean_model.F90:1903-1911): interior neighbours,
+ * cyclic wrap, folded north edge; wall halos are left untouched.  Device pointers, data-domain layout.        */
+int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const double *rho_dzt_taum1,
+                              const double *rho_dztr_taup1, const double *const *T_taum1,
+                              const double *const *th_tendency, double *const *T_taup1, void *stream);
+
 /* ---- metrics on device arrays ---------------------------------------------------------------------------
  * mom5adv_chksum_dev: mpp_chksum of the compute domain (wrap-around sum of the int64 bit patterns,
  * mpp_chksum_int.h:20-38), this rank's share; masked != 0 multiplies by tmask first

@@ -159,6 +159,12 @@ class TracerAdvect:
         else:
             check(self.L.mom5adv_vert(*args), "mom5adv_vert")
 
+    # ---- tracer time update + halo-1 update (ocean_tracer.F90:2341-2350, ocean_model.F90:1903-1911) ----
+    def tracer_update(self, T_taum1: Sequence, th_tendency: Sequence, T_taup1: Sequence, rho_dzt_taum1, rho_dztr_taup1,
+                      dtime: float):
+        check(self.L.mom5adv_tracer_update_dev(self.handle, len(T_taum1), float(dtime), _ptr(rho_dzt_taum1), _ptr(rho_dztr_taup1),
+                                               _pp(T_taum1), _pp(th_tendency), _pp(T_taup1), _cur_stream()), "tracer_update_dev")
+
     # ---- metrics ----
     def chksum(self, field, masked: bool = False) -> int:
         out = C.c_int64(0)

@@ -44,5 +44,7 @@ def build(force: bool = False, fma: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, fma="--fma" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    # default: both flavours (the bit-exact library and the FMA tolerance build used by one test)
+    flavours = [True] if "--fma" in sys.argv else [False] if "--no-fma" in sys.argv or "-v" in sys.argv else [False, True]
+    for f in flavours:
+        print(build(force="--force" in sys.argv, fma=f, verbose="-v" in sys.argv))

@@ -93,6 +93,7 @@ struct mom5adv_ctx {
     std::vector<double *> tmA, tmB;    // h2 scratch per tracer
     // halo machinery
     HaloPlan plan[4];                  // indexed by flags (1 = X, 2 = Y, 3 = XY)
+    HaloPlan plan1;                    // halo-1 full update of data-domain arrays (field(taup1), OM:1903-1911)
     double *sendbuf = 0, *recvbuf = 0;
     size_t bufcap = 0;
     // host-pointer mode mirrors
@@ -329,9 +330,10 @@ extern "C" int mom5adv_comm_destroy(mom5adv_comm c)
 // ------------------------------------------------------------------------------------------------
 // halo update of nf h2 fields
 // ------------------------------------------------------------------------------------------------
-static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags, cudaStream_t st)
+template <int LAYOUT>
+static int halo_update_l(mom5adv_ctx *h, double *const *fields, int nf, int flags, cudaStream_t st)
 {
-    const HaloPlan &P = h->plan[flags & 3];
+    const HaloPlan &P = (LAYOUT == 0) ? h->plan[flags & 3] : h->plan1;
     const int nk = h->g.nk;
     for (int f0 = 0; f0 < nf; f0 += HALO_MAXF) {
         const int nfc = std::min(HALO_MAXF, nf - f0);
@@ -348,7 +350,7 @@ static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags,
             if (A.nmsg == 0) return;
             A.total = A.start[A.nmsg];
             const int nb = (int)std::min<long long>((A.total + 255) / 256, 148 * 16);
-            LAUNCH(h, k_halo<0>, nb, 256, 0, st, h->g, A);
+            LAUNCH(h, (k_halo<0, LAYOUT>), nb, 256, 0, st, h->g, A);
             A.nmsg = 0;
         };
         L.nmsg = 0; L.start[0] = 0;
@@ -413,7 +415,7 @@ static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags,
         R.buf = h->recvbuf;
         if (S.total) {
             const int nb = (int)std::min<long long>((S.total + 255) / 256, 148 * 16);
-            LAUNCH(h, k_halo<1>, nb, 256, 0, st, h->g, S);
+            LAUNCH(h, (k_halo<1, LAYOUT>), nb, 256, 0, st, h->g, S);
         }
         ncclComm_t comm = (ncclComm_t)h->comm->nccl;
         NCCL_NEED();
@@ -433,11 +435,16 @@ static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags,
         NCCL_TRY(N->GroupEnd());
         if (R.total) {
             const int nb = (int)std::min<long long>((R.total + 255) / 256, 148 * 16);
-            LAUNCH(h, k_halo<2>, nb, 256, 0, st, h->g, R);
+            LAUNCH(h, (k_halo<2, LAYOUT>), nb, 256, 0, st, h->g, R);
         }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+static int halo_update(mom5adv_ctx *h, double *const *fields, int nf, int flags, cudaStream_t st)
+{
+    return halo_update_l<0>(h, fields, nf, flags, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -525,6 +532,7 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     for (int e = 0; e < 6; e++) CUDA_TRY(cudaEventCreate(&h->ev[e]));
     DomInfo D{h->ni_g, h->nj_g, h->px, h->py, h->cyclic_x, h->cyclic_y, h->tripolar, &h->ibeg, &h->iend, &h->jbeg, &h->jend};
     for (int f = 1; f <= 3; f++) build_plan(D, h->rank, f, 2, h->plan[f]);
+    build_plan(D, h->rank, 3, 1, h->plan1);
 
     // tmask_mdfl == tmask_quick: compute domain := Grd%tmask, full halo-2 update (OTA:1668-1675, 1478-1487), stored as u8
     cudaStream_t st = h->stream;
@@ -1059,6 +1067,29 @@ extern "C" int mom5adv_vert(mom5adv_handle h, int scheme, const double *Tm1, con
     if (fz) D2H(fz, dfz, N);
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumer of the tendencies: tracer time update + halo-1 update (ocean_tracer.F90:2341-2350, ocean_model.F90:1903-1911)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const double *rho_dzt_taum1,
+                                         const double *rho_dztr_taup1, const double *const *T_taum1,
+                                         const double *const *th_tendency, double *const *T_taup1, void *stream)
+{
+    if (!h || !rho_dzt_taum1 || !rho_dztr_taup1 || !T_taum1 || !th_tendency || !T_taup1 || ntr < 1) {
+        set_error("mom5adv_tracer_update_dev: bad argument");
+        return MOM5ADV_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom &g = h->g;
+    for (int n0 = 0; n0 < ntr; n0 += MAXNT) {
+        UpdArgs<MAXNT> a{};
+        for (int q = 0; q < MAXNT && n0 + q < ntr; q++) { a.T[q] = T_taum1[n0 + q]; a.th[q] = th_tendency[n0 + q]; a.Tnew[q] = T_taup1[n0 + q]; }
+        a.rho_m1 = rho_dzt_taum1; a.rho_r = rho_dztr_taup1; a.dtime = dtime;
+        LAUNCH(h, k_tracer_update<MAXNT>, dim3((g.ni + 127) / 128, g.nj, g.nk), 128, 0, st, g, a);
+    }
+    std::vector<double *> f(T_taup1, T_taup1 + ntr);
+    return halo_update_l<1>(h, f.data(), ntr, 3, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,7 +36,11 @@ struct CopyArgs {
 };
 
 // mode 0: local copy (src rect -> dst rect, same rank); 1: pack (src rect -> buf); 2: unpack (buf -> dst rect)
-template <int MODE>
+// LAYOUT 0: h2 scratch fields (halo 2, t3 indexing); LAYOUT 1: caller's data-domain arrays (halo 1, d3 indexing)
+template <int LAYOUT>
+__device__ __forceinline__ size_t halo_idx(const Geom &g, int i, int j, int k) { return LAYOUT == 0 ? t3(g, i, j, k) : d3(g, i, j, k); }
+
+template <int MODE, int LAYOUT>
 __global__ void k_halo(const Geom g, const CopyArgs a)
 {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.total; e += (long long)gridDim.x * blockDim.x) {
@@ -52,10 +56,31 @@ __global__ void k_halo(const Geom g, const CopyArgs a)
         const int si = d.si0 + p, sj = d.sj0 + q;
         const int di = d.flip ? d.di0 + (d.w - 1 - p) : d.di0 + p;
         const int dj = d.flip ? d.dj0 + (d.h - 1 - q) : d.dj0 + q;
-        if (MODE == 0) a.f[n][t3(g, di, dj, k)] = a.f[n][t3(g, si, sj, k)];
-        if (MODE == 1) a.buf[d.off + (e - a.start[m])] = a.f[n][t3(g, si, sj, k)];
-        if (MODE == 2) a.f[n][t3(g, di, dj, k)] = a.buf[d.off + (e - a.start[m])];
+        if (MODE == 0) a.f[n][halo_idx<LAYOUT>(g, di, dj, k)] = a.f[n][halo_idx<LAYOUT>(g, si, sj, k)];
+        if (MODE == 1) a.buf[d.off + (e - a.start[m])] = a.f[n][halo_idx<LAYOUT>(g, si, sj, k)];
+        if (MODE == 2) a.f[n][halo_idx<LAYOUT>(g, di, dj, k)] = a.buf[d.off + (e - a.start[m])];
     }
+}
+
+// field(taup1) = (rho_dzt(taum1)*field(taum1) + dtime*th_tendency)*rho_dztr(taup1)   (ocean_tracer.F90:2341-2350)
+template <int NT>
+struct UpdArgs {
+    const double *T[NT], *th[NT];
+    double *Tnew[NT];
+    const double *rho_m1, *rho_r;
+    double dtime;
+};
+template <int NT>
+__global__ void __launch_bounds__(128) k_tracer_update(const Geom g, const UpdArgs<NT> a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > g.ni) return;
+    const size_t q = d3(g, i, j, k);
+    const double r0 = a.rho_m1[q], rr = a.rho_r[q];
+#pragma unroll
+    for (int n = 0; n < NT; n++)
+        if (a.Tnew[n]) a.Tnew[n][q] = ((r0 * a.T[n][q]) + (a.dtime * a.th[n][q])) * rr;
 }
 
 // compute-domain copy between a data-domain array and an h2 field (tracer_quick / tmask staging)

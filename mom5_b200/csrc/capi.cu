@@ -505,6 +505,11 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     g.nxd = g.ni + 2; g.nyd = g.nj + 2; g.slab = (long long)g.nxd * g.nyd;
     g.tpitch = ((g.ni + TOFF + 3) + 15) / 16 * 16; g.tslab = (long long)g.tpitch * (g.nj + 4);
     g.mpitch = g.tpitch; g.mslab = g.tslab;
+    if ((unsigned long long)g.tslab * (unsigned long long)g.nk >= (1ull << 32) || (unsigned long long)g.slab * (unsigned long long)(g.nk + 2) >= (1ull << 32)) {
+        set_error("mom5adv_init: local block too large (the kernels index with 32-bit element offsets: < 2^32 elements per array)");
+        delete h;
+        return MOM5ADV_EUNSUP;
+    }
     const size_t n2 = (size_t)g.slab;
     if (upload(&h->dat, G->dat, n2) || upload(&h->datr, G->datr, n2) || upload(&h->dxte, G->dxte, n2) ||
         upload(&h->dyte, G->dyte, n2) || upload(&h->dxtn, G->dxtn, n2) || upload(&h->dytn, G->dytn, n2) ||

@@ -78,7 +78,7 @@ __device__ __forceinline__ unsigned z_level(ZLevel<NT> &L)
 {
     unsigned bad = 0;
     const Div<EXACT> rr = Div<EXACT>::make(L.r, bad);
-    const FaceCoef c = make_coef<EXACT>(L.dat * L.wk, fabs(rr(L.wk * L.dtime, bad)), nib_and(L.nb, 6u), bad);
+    const FaceCoef c = make_coef<EXACT>(L.dat * L.wk, fabs(rr.template operator()<false>(L.wk * L.dtime, bad)), nib_and(L.nb, 6u), bad);
     const double mm12 = nib_and(L.nb, 12u);           // m(kp1)*m(kp2)
     const double dtr = (VAR == VAR_ONE) ? rr(L.dtime, bad) : 0.0;
 #pragma unroll
@@ -111,15 +111,18 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
     const int k0 = ks > 1 ? ks - 1 : 1;  // first face evaluated (warm-up face when the chunk starts below the surface)
-    const size_t c2 = d2(g, i, j);
-    const size_t slab = (size_t)g.slab;
+    // element offsets are kept in 32 bits (every array of this path has < 2^32 elements, checked in mom5adv_init):
+    // one IMAD.WIDE per address instead of a 64-bit add chain
+    typedef unsigned ofs_t;
+    const ofs_t c2 = (ofs_t)d2(g, i, j);
+    const ofs_t slab = (ofs_t)g.slab;
 
-    size_t qd = d3(g, i, j, k0);                                  // data-domain offset of level k
-    size_t qt = t3(g, i, j, k0);                                  // h2 offset of level k
-    size_t q2 = qd + slab * (size_t)(min(k0 + 2, g.nk) - k0);     // data-domain offset of level min(k+2, nk)
-    const size_t qkm = (k0 > 1) ? qd - slab : qd, qkp = (k0 < g.nk) ? qd + slab : qd;
+    ofs_t qd = (ofs_t)d3(g, i, j, k0);                            // data-domain offset of level k
+    ofs_t qt = (ofs_t)t3(g, i, j, k0);                            // h2 offset of level k
+    ofs_t q2 = qd + slab * (ofs_t)(min(k0 + 2, g.nk) - k0);       // data-domain offset of level min(k+2, nk)
+    const ofs_t qkm = (k0 > 1) ? qd - slab : qd, qkp = (k0 < g.nk) ? qd + slab : qd;
 
-    auto stage = [&](int st, size_t qd_, size_t q2_) {   // operands of the level whose offsets are (qd_, q2_)
+    auto stage = [&](int st, ofs_t qd_, ofs_t q2_) {   // operands of the level whose offsets are (qd_, q2_)
 #pragma unroll
         for (int n = 0; n < NT; n++) cp_async8(&sm[st][n][tx], a.T[n] + q2_);
         cp_async8(&sm[st][NT][tx], a.w + qd_ + slab);             // w3(k) = d3(k) + slab
@@ -146,8 +149,8 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
 #pragma unroll 3
     for (int k = k0; k <= ke; k++, st ^= 1) {
         // ---- stage the operands of level k+1 (each thread reads back only what it staged itself) ----
-        const size_t qd_n = qd + slab;
-        const size_t q2_n = (k + 3 <= g.nk) ? q2 + slab : q2;
+        const ofs_t qd_n = qd + slab;
+        const ofs_t q2_n = (k + 3 <= g.nk) ? q2 + slab : q2;
         unsigned nb_n = 0;
         if (k < ke) {
             stage(st ^ 1, qd_n, q2_n);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
         L.nb = nb_n;
         qd = qd_n;
         q2 = q2_n;
-        qt += (size_t)g.tslab;
+        qt += (ofs_t)g.tslab;
     }
 }
 
@@ -206,7 +209,7 @@ __device__ __forceinline__ unsigned x_face(XFace<NT> &L)
 {
     unsigned bad = 0;
     L.mf = L.dyte * L.uu;
-    const FaceCoef c = make_coef<EXACT>(L.mf, fabs(Div<EXACT>::make((L.rho_i + L.rho_e) * L.dxte, bad)((L.uu * L.dtime) * 2.0, bad)),
+    const FaceCoef c = make_coef<EXACT>(L.mf, fabs(Div<EXACT>::make((L.rho_i + L.rho_e) * L.dxte, bad).template operator()<false>((L.uu * L.dtime) * 2.0, bad)),
                                         nib_and(L.nb, 6u), bad);
     const double mm01 = nib_and(L.nb, 3u), mm23 = nib_and(L.nb, 12u);
 #pragma unroll
@@ -263,19 +266,20 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
     const int ic = min(i, g.ni);                         // clamped index for the loads of idle lanes
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
-    const size_t c2 = d2(g, ic, j);
+    typedef unsigned ofs_t;   // 32-bit element offsets (see k_sweby_z)
+    const ofs_t c2 = (ofs_t)d2(g, ic, j);
     XFace<NT> F;
     XCell<NT> C;
     F.dyte = a.dyte[c2]; F.dxte = a.dxte[c2]; F.dtime = a.dtime; F.sl = a.sl;
     C.datr = a.datr[c2]; C.dtime = a.dtime;
-    const size_t slab = (size_t)g.slab, tslab = (size_t)g.tslab;
-    size_t q = d3(g, ic, j, ks);
+    const ofs_t slab = (ofs_t)g.slab, tslab = (ofs_t)g.tslab;
+    ofs_t q = (ofs_t)d3(g, ic, j, ks);
     // staged elements: tm element e = iw-1+lane (slot lane) and, for lanes 0..2, iw+31+lane (slot 32+lane);
     // rho element iw+lane (slot lane) and, for lane 0, iw+32 (slot 32); T, u at ic (slot lane)
-    size_t tqa = t3(g, min(iw - 1 + lane, g.ni + 2), j, ks);
-    size_t tqb = t3(g, min(iw + 31 + lane, g.ni + 2), j, ks);
-    size_t qr = d3(g, min(iw + lane, g.ni + 1), j, ks);
-    size_t qrb = d3(g, min(iw + 32, g.ni + 1), j, ks);
+    ofs_t tqa = (ofs_t)t3(g, min(iw - 1 + lane, g.ni + 2), j, ks);
+    ofs_t tqb = (ofs_t)t3(g, min(iw + 31 + lane, g.ni + 2), j, ks);
+    ofs_t qr = (ofs_t)d3(g, min(iw + lane, g.ni + 1), j, ks);
+    ofs_t qrb = (ofs_t)d3(g, min(iw + 32, g.ni + 1), j, ks);
 
     auto stage = [&](int st) {
 #pragma unroll
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
     for (int k = ks; k <= ke; k++, st ^= 1) {
         __syncwarp();                                    // everyone is done reading the stage we are about to refill
         unsigned nb_n = 0;
-        const size_t q_cur = q, tq_cur = tqa + 1;        // tm(i) lives one element right of the lane's staged element
+        const ofs_t q_cur = q, tq_cur = tqa + 1;        // tm(i) lives one element right of the lane's staged element
         if (k < ke) {
             q += slab; qr += slab; qrb += slab; tqa += tslab; tqb += tslab;
             stage(st ^ 1);
@@ -364,7 +368,7 @@ __device__ __forceinline__ unsigned y_level(YLevel<NT> &L)
 {
     unsigned bad = 0;
     const double mf = L.dxtn * L.vv;
-    const FaceCoef c = make_coef<EXACT>(mf, fabs(Div<EXACT>::make((L.rho0 + L.rho1) * L.dytn, bad)((L.vv * L.dtime) * 2.0, bad)),
+    const FaceCoef c = make_coef<EXACT>(mf, fabs(Div<EXACT>::make((L.rho0 + L.rho1) * L.dytn, bad).template operator()<false>((L.vv * L.dtime) * 2.0, bad)),
                                         nib_and(L.nb, 6u), bad);
     const double mm23 = nib_and(L.nb, 12u), m0 = nib_and(L.nb, 2u);
 #pragma unroll
@@ -415,15 +419,16 @@ __global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const 
     const int i = min(i_raw, g.ni);
     const int js = jc * a.kc + 1;
     const int je = min(js + a.kc - 1, g.nj);
-    const size_t nxd = (size_t)g.nxd, tp = (size_t)g.tpitch;
-    const size_t wofs = (size_t)g.slab;    // w3(k) = d3(k) + slab ; w3(k-1) = d3(k)
+    typedef unsigned ofs_t;   // 32-bit element offsets (see k_sweby_z)
+    const ofs_t nxd = (ofs_t)g.nxd, tp = (ofs_t)g.tpitch;
+    const ofs_t wofs = (ofs_t)g.slab;    // w3(k) = d3(k) + slab ; w3(k-1) = d3(k)
     const bool has_km1 = (k > 1);
 
-    size_t q = d3(g, i, js - 1, k);        // data-domain offset of (i, jf, k)
-    size_t c2 = d2(g, i, js - 1);
-    size_t tq = t3(g, i, js - 1, k);
+    ofs_t q = (ofs_t)d3(g, i, js - 1, k);        // data-domain offset of (i, jf, k)
+    ofs_t c2 = (ofs_t)d2(g, i, js - 1);
+    ofs_t tq = (ofs_t)t3(g, i, js - 1, k);
 
-    auto stage = [&](int st, size_t qq, size_t cc, size_t tt) {   // operands of the iteration at face row jf (offsets of that row)
+    auto stage = [&](int st, ofs_t qq, ofs_t cc, ofs_t tt) {   // operands of the iteration at face row jf (offsets of that row)
         double(*S)[YROW] = sm[st][wy];
 #pragma unroll
         for (int n = 0; n < NT; n++) {

@@ -136,6 +136,15 @@ int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const dou
                               const double *rho_dztr_taup1, const double *const *T_taum1,
                               const double *const *th_tendency, double *const *T_taup1, void *stream);
 
+/* ---- producer of wrho_bt ----------------------------------------------------------
+ * diverge_t(:,:,k) = tmask*(BDX_ET(uhrho_et) + BDY_NT(vhrho_nt)) and the continuity recurrence
+ * wrho_bt(:,:,k) = ((rho_dzt_tendency - mass_source) + diverge_t(:,:,k) + wrho_bt(:,:,k-1))*tmask over the whole data
+ * domain (ocean_advection_velocity.F90:660-669; ocean_operators.F90:945-958, 1230-1243).  wrho_bt(:,:,0) = -(pme+river)
+ * must be set by the caller; rho_dzt_tendency / mass_source / diverge_t may be NULL (zero arrays / not wanted).     */
+int mom5adv_continuity_dev(mom5adv_handle h, const double *uhrho_et, const double *vhrho_nt,
+                           const double *rho_dzt_tendency, const double *mass_source, double *wrho_bt,
+                           double *diverge_t, void *stream);
+
 /* ---- metrics on device arrays ---------------------------------------------------------------------------
  * mom5adv_chksum_dev: mpp_chksum of the compute domain (wrap-around sum of the int64 bit patterns,
  * mpp_chksum_int.h:20-38), this rank's share; masked != 0 multiplies by tmask first

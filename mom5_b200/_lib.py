@@ -40,6 +40,7 @@ SYMBOLS = {
     "mom5adv_vert": (C.c_int, [_v, C.c_int, dp, dp, dp, dp, dp, dp, dp]),
     "mom5adv_vert_dev": (C.c_int, [_v, C.c_int, dp, dp, dp, dp, dp, dp, dp, _v]),
     "mom5adv_tracer_update_dev": (C.c_int, [_v, C.c_int, C.c_double, dp, dp, dpp, dpp, dpp, _v]),
+    "mom5adv_continuity_dev": (C.c_int, [_v, dp, dp, dp, dp, dp, dp, _v]),
     "mom5adv_chksum_dev": (C.c_int, [_v, dp, C.c_int, C.POINTER(C.c_int64), _v]),
     "mom5adv_total_tracer_dev": (C.c_int, [_v, dp, dp, dp, _v]),
     "mom5adv_last_timing_ms": (C.c_int, [_v, C.POINTER(C.c_float)]),

@@ -165,6 +165,11 @@ class TracerAdvect:
         check(self.L.mom5adv_tracer_update_dev(self.handle, len(T_taum1), float(dtime), _ptr(rho_dzt_taum1), _ptr(rho_dztr_taup1),
                                                _pp(T_taum1), _pp(th_tendency), _pp(T_taup1), _cur_stream()), "tracer_update_dev")
 
+    # ---- continuity: wrho_bt from the horizontal transports (ocean_advection_velocity.F90:660-669) ----
+    def continuity(self, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tendency=None, mass_source=None, diverge_t=None):
+        check(self.L.mom5adv_continuity_dev(self.handle, _ptr(uhrho_et), _ptr(vhrho_nt), _ptr(rho_dzt_tendency), _ptr(mass_source),
+                                            _ptr(wrho_bt), _ptr(diverge_t), _cur_stream()), "continuity_dev")
+
     # ---- metrics ----
     def chksum(self, field, masked: bool = False) -> int:
         out = C.c_int64(0)

@@ -1098,6 +1098,21 @@ extern "C" int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime
 }
 
 // ------------------------------------------------------------------------------------------------
+// producer of wrho_bt: continuity (ocean_advection_velocity.F90:660-669)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_continuity_dev(mom5adv_handle h, const double *uhrho_et, const double *vhrho_nt,
+                                      const double *rho_dzt_tendency, const double *mass_source, double *wrho_bt,
+                                      double *diverge_t, void *stream)
+{
+    if (!h || !uhrho_et || !vhrho_nt || !wrho_bt) { set_error("mom5adv_continuity_dev: null argument"); return MOM5ADV_EINVAL; }
+    const Geom &g = h->g;
+    LAUNCH(h, k_continuity, dim3((g.ni + 2 + 127) / 128, g.nj + 2), 128, 0, (cudaStream_t)stream, g, h->tmask, h->dyte, h->dxtn,
+           h->datr, uhrho_et, vhrho_nt, rho_dzt_tendency, mass_source, wrho_bt, diverge_t);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // metrics
 // ------------------------------------------------------------------------------------------------
 __global__ void k_chksum(const Geom g, const double *__restrict__ f, const double *__restrict__ tmask, unsigned long long *out)

@@ -278,3 +278,35 @@ static int vert_dev(const Geom &g, const QuickW &q, const double *tmask, const d
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ---- continuity on the T grid ----
+//   diverge_t = tmask*(BDX_ET(uhrho_et) + BDY_NT(vhrho_nt))                          ocean_advection_velocity.F90:660
+//   BDX_ET(i,j) = (dyte(i,j)*a(i,j) - dyte(i-1,j)*a(i-1,j))*datr(i,j), 0 at i = isd   ocean_operators.F90:945-958
+//   BDY_NT(i,j) = (dxtn(i,j)*a(i,j) - dxtn(i,j-1)*a(i,j-1))*datr(i,j), 0 at j = jsd   ocean_operators.F90:1230-1243
+//   wrho_bt(k) = ((rho_dzt_tendency - mass_source) + diverge_t(k) + wrho_bt(k-1))*tmask                         :666-669
+// one thread per data-domain column marching down k; wrho_bt(:,:,0) is the caller's.
+__global__ void __launch_bounds__(128)
+k_continuity(const Geom g, const double *__restrict__ tmask, const double *__restrict__ dyte, const double *__restrict__ dxtn,
+             const double *__restrict__ datr, const double *__restrict__ u, const double *__restrict__ v,
+             const double *__restrict__ tend, const double *__restrict__ src, double *__restrict__ w, double *__restrict__ div_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni+1
+    const int j = blockIdx.y;                              // 0..nj+1
+    if (i > g.ni + 1) return;
+    const size_t c2 = d2(g, i, j);
+    const double dr = datr[c2], dye = dyte[c2], dxn = dxtn[c2];
+    const double dyw = (i >= 1) ? dyte[c2 - 1] : 0.0, dxs = (j >= 1) ? dxtn[c2 - g.nxd] : 0.0;
+    double wk = w[w3(g, i, j, 0)];
+    for (int k = 1; k <= g.nk; k++) {
+        const size_t c = d3(g, i, j, k);
+        double bdx = 0.0, bdy = 0.0;
+        if (i >= 1) bdx = ((dye * u[c]) - (dyw * u[c - 1])) * dr;
+        if (j >= 1) bdy = ((dxn * v[c]) - (dxs * v[c - g.nxd])) * dr;
+        const double m = tmask[c];
+        const double dv = m * (bdx + bdy);
+        const double tmp = (tend ? tend[c] : 0.0) - (src ? src[c] : 0.0);
+        if (div_out) div_out[c] = dv;
+        wk = ((tmp + dv) + wk) * m;
+        w[w3(g, i, j, k)] = wk;
+    }
+}

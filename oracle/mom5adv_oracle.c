@@ -794,6 +794,32 @@ void orc_tracer_update(const orc_block *b, double dtime, const double *rho_taum1
             }
 }
 
+/* continuity on the T-grid:
+ *   diverge_t(:,:,k) = tmask*(BDX_ET(uhrho_et) + BDY_NT(vhrho_nt))                   ocean_advection_velocity.F90:660
+ *   BDX_ET(i,j) = (dyte(i,j)*a(i,j) - dyte(i-1,j)*a(i-1,j))*datr(i,j), 0 at i = isd   ocean_operators.F90:945-958
+ *   BDY_NT(i,j) = (dxtn(i,j)*a(i,j) - dxtn(i,j-1)*a(i,j-1))*datr(i,j), 0 at j = jsd   ocean_operators.F90:1230-1243
+ *   wrho_bt(:,:,k) = (tmp + diverge_t(:,:,k) + wrho_bt(:,:,k-1))*tmask,  tmp = rho_dzt_tendency - mass_source   :666-669
+ * over the whole data domain; wrho_bt(:,:,0) is the caller's (-(pme+river), :664).  tend/src may be NULL (= zero arrays). */
+void orc_continuity(const orc_block *b, const double *u, const double *v, const double *tend, const double *src,
+                    double *w, double *diverge_t)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    for (int k = 1; k <= nk; k++)
+        for (int j = 0; j <= nj + 1; j++)
+            for (int i = 0; i <= ni + 1; i++) {
+                double bdx = 0.0, bdy = 0.0;
+                if (i >= 1)
+                    bdx = ((b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)]) - (b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)])) * b->datr[D2(b, i, j)];
+                if (j >= 1)
+                    bdy = ((b->dxtn[D2(b, i, j)] * v[D3(b, i, j, k)]) - (b->dxtn[D2(b, i, j - 1)] * v[D3(b, i, j - 1, k)])) * b->datr[D2(b, i, j)];
+                const double m = b->tmask[D3(b, i, j, k)];
+                const double div = m * (bdx + bdy);
+                const double tmp = (tend ? tend[D3(b, i, j, k)] : 0.0) - (src ? src[D3(b, i, j, k)] : 0.0);
+                if (diverge_t) diverge_t[D3(b, i, j, k)] = div;
+                w[W3(b, i, j, k)] = ((tmp + div) + w[W3(b, i, j, k - 1)]) * m;
+            }
+}
+
 /* MPPI/mpp_chksum_int.h:20-38 + mpp_chksum.h:20-41: wrap-around sum of the int64 bit patterns */
 int64_t orc_chksum(const double *a, int ni, int nj, int nk, int halo, const double *mask)
 {

@@ -128,6 +128,10 @@ void orc_accumulate(const orc_block *b, const double *wrk1, double *th_tendency)
 void orc_tracer_update(const orc_block *b, double dtime, const double *rho_dzt_taum1, const double *rho_dztr_taup1,
                        const double *T_taum1, const double *th_tendency, double *T_taup1);
 
+/* ---- continuity: diverge_t and wrho_bt from the horizontal transports (ocean_advection_velocity.F90:660-669) ---- */
+void orc_continuity(const orc_block *b, const double *uhrho_et, const double *vhrho_nt, const double *rho_dzt_tendency,
+                    const double *mass_source, double *wrho_bt, double *diverge_t);
+
 /* ---- metrics ---- */
 int64_t orc_chksum(const double *a, int ni, int nj, int nk, int halo, const double *mask_or_null);
     /* mpp_chksum_int.h:20-38 on the compute domain; with mask: chksum(a*mask) (ocean_tracer_util.F90:562-566) */

@@ -292,6 +292,16 @@ class Oracle:
             self.L.orc_vert_upwind(C.byref(b.c), _ptr(T[ib]), _ptr(self.w[ib]), _ptr(fz[ib]), _ptr(wrk1[ib]))
         return dict(wrk1=wrk1, flux_z=fz)
 
+    # ---- continuity (one block at a time; no halo exchange involved) ----
+    def continuity(self, ib: int, u, v, w, tend=None, src=None):
+        """w: (nk+1, ny, nx) with level 0 preset; returns (w, diverge_t)"""
+        b = self.blocks[ib]
+        u, v = _np(u), _np(v)
+        w = np.array(_np(w), copy=True)
+        div = b.d1()
+        self.L.orc_continuity(C.byref(b.c), _ptr(u), _ptr(v), _ptr(_np(tend)), _ptr(_np(src)), _ptr(w), _ptr(div))
+        return w, div
+
     # ---- metrics ----
     def chksum(self, fields: List[np.ndarray], halo: int = 1, masked: bool = False) -> int:
         s = 0

@@ -378,6 +378,10 @@ def parse_decls(lines: List[str]):
         if not m:
             continue
         dims, attrs = m.group("dims"), (m.group("attrs") or "").lower()
+        if dims is None:   # `real, intent(in), dimension(isd:,jsd:) :: a` -- dimension after other attributes
+            md = re.search(r"dimension\s*\((.*?)\)\s*(,|$)", m.group("attrs") or "", flags=re.I)
+            if md:
+                dims = md.group(1)
         names = [n.strip() for n in _split_top(m.group("names"), ",")]
         for nm in names:
             d = dims

@@ -41,6 +41,8 @@ from mom5_b200.synthetic import make_case  # noqa: E402
 
 OTA = "/root/reference/src/mom5/ocean_tracers/ocean_tracer_advect.F90"
 OPARAM = "/root/reference/src/mom5/ocean_core/ocean_parameters.F90"
+OAV = "/root/reference/src/mom5/ocean_core/ocean_advection_velocity.F90"
+OOP = "/root/reference/src/mom5/ocean_core/ocean_operators.F90"
 
 GOLDEN_CASES = {
     # name -> (synthetic case, overrides)
@@ -295,6 +297,37 @@ def run_case(name):
         out[f"{tag}.flux_z"] = env["flux_z"].a.copy()
         out[f"{tag}.tracer"] = np.array(n)
         print(f"  {tag}: {time.time() - t0:.1f}s")
+
+    # ---- continuity: diverge_t + wrho_bt recurrence (ocean_advection_velocity.F90 C-grid block; BDX_ET / BDY_NT) ----
+    osrc = open(OOP).read().split("\n")
+    vsrc = open(OAV).read().split("\n")
+    env["halo"] = 1
+    for nm in ("BDX_ET", "BDY_NT"):
+        f0, l0 = find_routine(osrc, "function", nm)
+        code, _ = translate_routine(osrc, f0, l0, array_names=arrays)
+        exec(compile(code, f"<ocean_operators.F90:{f0}-{l0} {nm}>", "exec"), env)
+    ldiv = find_line(vsrc, r"Adv_vel%diverge_t\(:,:,k\) = Grd%tmask\(:,:,k\)\*\(BDX_ET")
+    lw0 = find_line(vsrc, r"Adv_vel%wrho_bt\(:,:,0\) = -\(pme", ldiv)
+    lw1 = next(n for n in range(lw0, len(vsrc) + 1) if re.match(r"\s*enddo", vsrc[n - 1]))
+    rng = np.random.default_rng(11)
+    shp2 = tuple(b.grid2d["dat"].shape)
+    env["pme"] = to_farray(1e-5 * rng.standard_normal(shp2), [0, 0])
+    env["river"] = to_farray(1e-6 * rng.standard_normal(shp2), [0, 0])
+    tend = 1e-4 * rng.standard_normal(tuple(b.rho_dzt.shape))
+    msrc = 1e-5 * rng.standard_normal(tuple(b.rho_dzt.shape))
+    env["Thickness"].rho_dzt_tendency = to_farray(tend, [0, 0, 1])
+    env["Thickness"].mass_source = to_farray(msrc, [0, 0, 1])
+    env["tmp"] = FArray([(0, s.ni + 1), (0, s.nj + 1)])
+    env["Adv_vel"].diverge_t = FArray([(0, s.ni + 1), (0, s.nj + 1), (1, s.nk)])
+    env["Adv_vel"].wrho_bt = FArray([(0, s.ni + 1), (0, s.nj + 1), (0, s.nk)])
+    snippet = ["do k=1,nk", vsrc[ldiv - 1], "enddo"] + vsrc[lw0 - 1:lw1]
+    code = translate_block(snippet, 1, len(snippet), array_names=arrays + ["tmp", "pme", "river"])
+    exec(compile(code, f"<ocean_advection_velocity.F90:{ldiv},{lw0}-{lw1} continuity>", "exec"), env)
+    out["continuity.diverge_t"] = env["Adv_vel"].diverge_t.a.copy()
+    out["continuity.wrho_bt"] = env["Adv_vel"].wrho_bt.a.copy()
+    out["continuity.in.tend"] = tend
+    out["continuity.in.src"] = msrc
+    print(f"  continuity: OAV:{ldiv},{lw0}-{lw1}")
 
     # ---- inputs ----
     inp = dict(ni=s.ni, nj=s.nj, nk=s.nk, ntr=ntr, dtime=s.dtime, cyclic_x=s.cyclic_x, cyclic_y=s.cyclic_y,

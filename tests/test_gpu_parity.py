@@ -205,6 +205,24 @@ def test_advection_only_time_stepping(case):
     adv.close()
 
 
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_continuity_vs_reference_golden(name):
+    """wrho_bt producer: diverge_t + continuity recurrence (ocean_advection_velocity.F90:660-669)"""
+    from mom5_b200.api import TracerAdvect
+    b, gold, _ = load_golden(name)
+    adv = TracerAdvect(b, ntracers_max=1)
+    w = torch.zeros(gold["continuity.wrho_bt"].shape, dtype=torch.float64)
+    w[0] = torch.from_numpy(gold["continuity.wrho_bt"][0])
+    w = w.cuda()
+    div = torch.full_like(_dev(b.rho_dzt), -777.0)
+    adv.continuity(_dev(b.uhrho_et), _dev(b.vhrho_nt), w, rho_dzt_tendency=torch.from_numpy(gold["continuity.in.tend"]).cuda(),
+                   mass_source=torch.from_numpy(gold["continuity.in.src"]).cuda(), diverge_t=div)
+    torch.cuda.synchronize()
+    assert_bit_equal(div, gold["continuity.diverge_t"], "diverge_t")
+    assert_bit_equal(w, gold["continuity.wrho_bt"], "wrho_bt")
+    adv.close()
+
+
 def test_device_metrics_match_the_oracle():
     """mpp_chksum (bit-pattern sum, mpp_chksum_int.h:20-38) and total_tracer (ocean_tracer_diag.F90:2405-2408)"""
     from mom5_b200.api import TracerAdvect

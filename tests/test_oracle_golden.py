@@ -112,3 +112,15 @@ def test_horz_vert_arms(name, tag):
     assert_bit_equal(th, gold[f"{tag}.horz.th_tendency"], "th after horz")
     o.L.orc_accumulate(C.byref(o.blocks[0].c), _ptr(v["wrk1"][0]), _ptr(th))
     assert_bit_equal(th, gold[f"{tag}.vert.th_tendency"], "th after vert")
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_continuity(name):
+    """diverge_t + wrho_bt recurrence (ocean_advection_velocity.F90:660-669, BDX_ET / BDY_NT) vs the reference text"""
+    b, gold, _ = load_golden(name)
+    _, o = _oracle(b)
+    w0 = np.zeros_like(gold["continuity.wrho_bt"])
+    w0[0] = gold["continuity.wrho_bt"][0]                  # wrho_bt(:,:,0) = -(pme + river) is the caller's
+    w, div = o.continuity(0, b.uhrho_et.numpy(), b.vhrho_nt.numpy(), w0, gold["continuity.in.tend"], gold["continuity.in.src"])
+    assert_bit_equal(div, gold["continuity.diverge_t"], "diverge_t")
+    assert_bit_equal(w, gold["continuity.wrho_bt"], "wrho_bt")

@@ -64,7 +64,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is None:
         fma = os.environ.get("MOM5ADV_FMA", "0") == "1"
-        path = FMA_LIB_PATH if fma else LIB_PATH
+        path = os.environ.get("MOM5ADV_LIB") or (FMA_LIB_PATH if fma else LIB_PATH)   # MOM5ADV_LIB: explicit build (tuning variants)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: build it with `python -m mom5_b200.build{' --fma' if fma else ''}` "
                                "(there is no CPU fallback for the advection path)")

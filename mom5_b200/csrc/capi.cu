@@ -111,6 +111,10 @@ struct mom5adv_ctx {
     int64_t launches = 0;
 };
 
+#ifndef YROWS_MAX
+#define YROWS_MAX 32
+#endif
+
 #define LAUNCH(h, kern, grid, block, smem, st, ...)  \
     do {                                             \
         kern<<<grid, block, smem, st>>>(__VA_ARGS__); \
@@ -709,7 +713,7 @@ static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     {
         const int YBX = 32 * YWARPS;
         const long long per_chunk = (long long)((g.ni + YBX - 1) / YBX) * YBX * g.nk;
-        int rows = 32;
+        int rows = YROWS_MAX;
         while (rows > 8 && per_chunk * ((g.nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
         h->y_rows = rows;
     }

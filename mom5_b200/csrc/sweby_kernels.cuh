@@ -63,7 +63,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // =================================================================================================
 // z sweep  (OTA:4150-4211 / 3843-3911)
 // =================================================================================================
+#ifndef ZBX
 #define ZBX 128
+#endif
+#ifndef ZMINB
+#define ZMINB 4
+#endif
+#ifndef XMINB
+#define XMINB 4
+#endif
+#ifndef YMINB
+#define YMINB 4
+#endif
 
 template <int NT>
 struct ZLevel {
@@ -100,7 +111,7 @@ template <int NT, int VAR>
 __device__ __noinline__ void z_level_exact(ZLevel<NT> *L) { z_level<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
-__global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArgs<NT> a)
+__global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const SwebyArgs<NT> a)
 {
     constexpr int NF = NT + 2;                           // T(kp2)[NT], w, rho of the next level
     __shared__ double sm[2][NF][ZBX];
@@ -194,7 +205,9 @@ __global__ void __launch_bounds__(ZBX, 4) k_sweby_z(const Geom g, const SwebyArg
 // =================================================================================================
 // x sweep  (OTA:4251-4299 / 3916-3969)
 // =================================================================================================
+#ifndef XWARPS
 #define XWARPS 4    // warps per block, stacked along j
+#endif
 #define XROW 36     // staged row: tm(i_w-1 .. i_w+33) = 35 values (+1 pad)
 
 template <int NT>
@@ -252,7 +265,7 @@ template <int NT, int VAR>
 __device__ __noinline__ void x_cell_exact(XCell<NT> *L) { x_cell<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
-__global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const SwebyArgs<NT> a)
+__global__ void __launch_bounds__(32 * XWARPS, XMINB) k_sweby_x(const Geom g, const SwebyArgs<NT> a)
 {
     constexpr int NF = 2 * NT + 2;                       // tm[NT], T[NT], u, rho
     __shared__ double sm[2][XWARPS][NF][XROW];
@@ -352,7 +365,9 @@ __global__ void __launch_bounds__(32 * XWARPS, 4) k_sweby_x(const Geom g, const 
 // =================================================================================================
 // y sweep + total tendency  (OTA:4362-4432 / 3980-4056)
 // =================================================================================================
+#ifndef YWARPS
 #define YWARPS 4
+#endif
 #define YROW 33     // staged row: element 0 = (i_w - 1), elements 1..32 = the lanes' own i
 
 template <int NT>
@@ -401,7 +416,7 @@ template <int NT, int VAR>
 __device__ __noinline__ void y_level_exact(YLevel<NT> *L) { y_level<NT, VAR, true>(*L); }
 
 template <int NT, int VAR, bool DIAG>
-__global__ void __launch_bounds__(32 * YWARPS, 4) k_sweby_y(const Geom g, const SwebyArgs<NT> a, const int nxt)
+__global__ void __launch_bounds__(32 * YWARPS, YMINB) k_sweby_y(const Geom g, const SwebyArgs<NT> a, const int nxt)
 {
     constexpr int NF = 3 * NT + 9;   // tm, T, th [NT each]; v, rho, u, wk, wkm1, dxtn, dytn, datr, dyte
     constexpr int F_T = NT, F_TH = 2 * NT, F_V = 3 * NT, F_RHO = F_V + 1, F_U = F_V + 2, F_WK = F_V + 3, F_WM = F_V + 4,

@@ -281,17 +281,33 @@ def run_gpu(args):
 
     peak, peak_src = measured_peaks()
     sb = sweep_bytes(ntr)
-    dom = max(("z", "x", "y"), key=lambda k: phase[k])
-    kname = {"z": "k_sweby_z", "x": "k_sweby_x", "y": "k_sweby_y"}[dom]
-    ach = cells * sb[dom] / (phase[dom] * 1e-3) / 1e9
+    fused = os.environ.get("MOM5ADV_FUSE", "1") != "0"
+    if fused:
+        # z sweep + ONE pass doing the x and y sweeps (k_sweby_xy): the pass does the algorithmic work of both sweeps
+        # (SURVEY.md section 8d counts 24*ntr+16 + 40*ntr+32 B per cell for them) while moving only the y sweep's bytes;
+        # phase "x" is the stand-alone x sweep on the 4 edge rows whose halo images the pass needs.
+        sb = dict(z=sb["z"], xy=sb["x"] + sb["y"])
+        phase_of = dict(z="z", xy="y")
+        kernels = dict(z="k_sweby_z", xy="k_sweby_xy")
+    else:
+        phase_of = dict(z="z", x="x", y="y")
+        kernels = dict(z="k_sweby_z", x="k_sweby_x", y="k_sweby_y")
+    dom = max(sb, key=lambda k: phase[phase_of[k]])
+    kname = kernels[dom]
+    ach = cells * sb[dom] / (phase[phase_of[dom]] * 1e-3) / 1e9
     roofline = dict(bound="hbm", kernel=kname, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
                     peak_source=peak_src,
-                    per_sweep={k: dict(ms=phase[k], alg_bytes_per_cell=sb[k], achieved_gbs=cells * sb[k] / (phase[k] * 1e-3) / 1e9)
-                               for k in ("z", "x", "y")},
+                    per_sweep={k: dict(kernel=kernels[k], ms=phase[phase_of[k]], alg_bytes_per_cell=sb[k],
+                                       achieved_gbs=cells * sb[k] / (phase[phase_of[k]] * 1e-3) / 1e9)
+                               for k in sb},
                     halo_ms=phase["halo"],
                     whole_call=dict(alg_bytes_per_cell_update=b_alg(ntr), achieved_gbs=value / world * b_alg(ntr) / 1e9,
                                     frac=value / world * b_alg(ntr) / 1e9 / peak))
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if fused:
+        roofline["per_sweep"]["xy"]["moved_bytes_per_cell"] = sweep_bytes(ntr)["y"]
+        roofline["per_sweep"]["xy"]["moved_gbs"] = cells * sweep_bytes(ntr)["y"] / (phase["y"] * 1e-3) / 1e9
+        roofline["edge_rows_x_ms"] = phase["x"]
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")   # ncu --set full DRAM bytes per launch, by kernel name
     if os.path.exists(traffic_file):
         try:
             roofline["traffic"] = json.load(open(traffic_file)).get(kname)
@@ -301,7 +317,7 @@ def run_gpu(args):
     res = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"{args.case}: {base.ni}x{base.nj}x{base.nk} per GPU, {ntr} tracers, Sweby MDFL advect_tracer_sweby_all "
-                                    f"(z,x,y sweeps + halo-2 updates), cyclic x + tripolar fold",
+                                    f"({'z sweep + fused x/y pass' if fused else 'z,x,y sweeps'} + halo-2 updates), cyclic x + tripolar fold",
                            global_grid=[spec.ni, spec.nj, spec.nk], layout=[px, py], tracers=ntr,
                            l2="inputs (>100 GB) far exceed the 126 MB L2; no flush needed", fmad=False,
                            setup_s=round(t_setup, 1)),

@@ -15,6 +15,7 @@
 #include "horz_vert_kernels.cuh"
 #include "mom5adv_internal.cuh"
 #include "sweby_kernels.cuh"
+#include "sweby_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -105,6 +106,8 @@ struct mom5adv_ctx {
     cudaEvent_t ev_sync[4];
     int overlap = 1;                   // MOM5ADV_OVERLAP=0 disables the comm/compute overlap
     int y_rows = 32;
+    int fuse = 1;                      // MOM5ADV_FUSE=0: three separate sweeps instead of z + fused x/y
+    int f_rows = 64;
     std::vector<cudaEvent_t> ev_up, ev_done;
     cudaEvent_t ev[6];
     bool ev_valid = false;
@@ -113,6 +116,9 @@ struct mom5adv_ctx {
 
 #ifndef YROWS_MAX
 #define YROWS_MAX 32
+#endif
+#ifndef FROWS_MAX
+#define FROWS_MAX 64
 #endif
 
 #define LAUNCH(h, kern, grid, block, smem, st, ...)  \
@@ -532,6 +538,7 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
     for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sync[e], cudaEventDisableTiming));
     if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
+    if (const char *fu = getenv("MOM5ADV_FUSE")) h->fuse = atoi(fu);
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
     h->ev_up.resize(ntracers_max); h->ev_done.resize(ntracers_max);
     for (int n = 0; n < ntracers_max; n++) {
@@ -600,35 +607,53 @@ static int pick_kchunk(const Geom &g, int per_level_threads)
     return (g.nk + nch - 1) / nch;
 }
 
-// part: 0 = whole sweep, 1 = interior tiles only (they read no halo), 2 = the two edge tiles (after the halo update)
+// A launch covers `count` tiles first, first+step, ... of the sweep's tiled dimension (z: i-tiles of ZBX columns,
+// x: i-tiles of 31 cells, y / fused xy: j-chunks); count < 0 = all of them.  x additionally takes a row range.
+struct Part {
+    int first = 0, step = 1, count = -1;
+    int row_first = 1, row_last = -1;   // x only; row_last < 0 = nj
+};
+enum { PH_Z = 0, PH_X = 1, PH_Y = 2, PH_XY = 3 };
+
 template <int NT, int VAR, bool DIAG>
-static void launch_group(mom5adv_ctx *h, int phase, int part, const SwebyArgs<NT> &a, cudaStream_t st)
+static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyArgs<NT> &a, cudaStream_t st)
 {
     const Geom &g = h->g;
     SwebyArgs<NT> b = a;
-    b.tile_first = 0; b.tile_step = 1;
-    if (phase == 0) {
+    b.tile_first = pt.first; b.tile_step = pt.step;
+    b.row_first = pt.row_first; b.row_last = pt.row_last < 0 ? g.nj : pt.row_last;
+    if (pt.count == 0) return 0;
+    if (phase == PH_Z) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
-        dim3 grid((g.ni + ZBX - 1) / ZBX, g.nj, (g.nk + b.kc - 1) / b.kc);
+        const int nzt = (g.ni + ZBX - 1) / ZBX;
+        dim3 grid(pt.count < 0 ? nzt : pt.count, g.nj, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, ZBX, 0, st, g, b);
-    } else if (phase == 1) {
+    } else if (phase == PH_X) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
         const int nxt = (g.ni + 30) / 31;
-        int ntile = nxt;
-        if (part == 1) { b.tile_first = 1; ntile = nxt - 2; }
-        if (part == 2) { b.tile_step = nxt - 1; ntile = 2; }
-        dim3 grid(ntile, (g.nj + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
+        const int nrows = b.row_last - b.row_first + 1;
+        if (nrows <= 0) return 0;
+        dim3 grid(pt.count < 0 ? nxt : pt.count, (nrows + XWARPS - 1) / XWARPS, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_x<NT, VAR, DIAG>), grid, dim3(32, XWARPS), 0, st, g, b);
-    } else {
+    } else if (phase == PH_Y) {
         const int YBX = 32 * YWARPS;
         const int nxt = (g.ni + YBX - 1) / YBX;
         b.kc = h->y_rows;
         const int njc = (g.nj + b.kc - 1) / b.kc;
-        int nch = njc;
-        if (part == 1) { b.tile_first = 1; nch = njc - 2; }
-        if (part == 2) { b.tile_step = njc - 1; nch = 2; }
-        LAUNCH(h, (k_sweby_y<NT, VAR, DIAG>), (unsigned)(g.nk * nxt * nch), YBX, 0, st, g, b, nxt);
+        LAUNCH(h, (k_sweby_y<NT, VAR, DIAG>), (unsigned)(g.nk * nxt * (pt.count < 0 ? njc : pt.count)), YBX, 0, st, g, b, nxt);
+    } else {
+        const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
+        b.kc = h->f_rows;
+        const int njc = (g.nj + b.kc - 1) / b.kc;
+        static bool attr_set = false;   // per instantiation
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedLayout<NT>::BYTES));
+            attr_set = true;
+        }
+        LAUNCH(h, (k_sweby_xy<NT, VAR, DIAG>), (unsigned)(g.nk * nxb * (pt.count < 0 ? njc : pt.count)), 32 * FWARPS,
+               FusedLayout<NT>::BYTES, st, g, b, nxb, nxt);
     }
+    return 0;
 }
 
 struct SwebyCall {
@@ -641,50 +666,60 @@ struct SwebyCall {
     int accumulate;
 };
 
+// diag_ok = false: never write diagnostics from this launch (edge-row x sweep ahead of the fused pass, which writes them)
 template <int NT>
-static void run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, int part, cudaStream_t st)
+static int run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, const Part &pt, bool diag_ok, cudaStream_t st)
 {
     SwebyArgs<NT> a{};
     bool diag = false;
-    double *const *fl = phase == 0 ? c.fz : phase == 1 ? c.fx : c.fy;
-    double *const *da = phase == 0 ? c.az : phase == 1 ? c.ax : c.ay;
+    double *const *fl = phase == PH_Z ? c.fz : phase == PH_Y ? c.fy : c.fx;
+    double *const *da = phase == PH_Z ? c.az : phase == PH_Y ? c.ay : c.ax;
     for (int n = 0; n < NT; n++) {
         a.T[n] = c.T[n0 + n];
-        if (phase == 0) { a.tm_in[n] = h->tmA[n0 + n]; }
-        if (phase == 1) { a.tm_in[n] = h->tmA[n0 + n]; a.tm_out[n] = h->tmB[n0 + n]; }
-        if (phase == 2) { a.tm_in[n] = h->tmB[n0 + n]; a.th[n] = c.th ? c.th[n0 + n] : nullptr; a.adv[n] = c.adv[n0 + n]; }
-        a.flux[n] = fl ? fl[n0 + n] : nullptr;
-        a.dadv[n] = da ? da[n0 + n] : nullptr;
-        diag |= (a.flux[n] != nullptr) || (a.dadv[n] != nullptr);
+        if (phase == PH_Z) { a.tm_in[n] = h->tmA[n0 + n]; }
+        if (phase == PH_X || phase == PH_XY) { a.tm_in[n] = h->tmA[n0 + n]; a.tm_out[n] = h->tmB[n0 + n]; }
+        if (phase == PH_Y) { a.tm_in[n] = h->tmB[n0 + n]; }
+        if (phase == PH_Y || phase == PH_XY) { a.th[n] = c.th ? c.th[n0 + n] : nullptr; a.adv[n] = c.adv[n0 + n]; }
+        if (diag_ok) {
+            a.flux[n] = fl ? fl[n0 + n] : nullptr;
+            a.dadv[n] = da ? da[n0 + n] : nullptr;
+            if (phase == PH_XY) {
+                a.flux2[n] = c.fy ? c.fy[n0 + n] : nullptr;
+                a.dadv2[n] = c.ay ? c.ay[n0 + n] : nullptr;
+            }
+        }
+        diag |= a.flux[n] || a.dadv[n] || a.flux2[n] || a.dadv2[n];
     }
     a.u = c.u; a.v = c.v; a.w = c.w; a.rho = c.rho;
-    a.nib = phase == 0 ? h->nibz : phase == 1 ? h->nibx : h->niby;
+    a.nib = phase == PH_Z ? h->nibz : phase == PH_Y ? h->niby : h->nibx;
+    a.nib2 = h->niby;
     a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
     a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;
     if (c.var == VAR_ALL) {
-        if (diag) launch_group<NT, VAR_ALL, true>(h, phase, part, a, st);
-        else launch_group<NT, VAR_ALL, false>(h, phase, part, a, st);
-    } else {
-        if (diag) launch_group<NT, VAR_ONE, true>(h, phase, part, a, st);
-        else launch_group<NT, VAR_ONE, false>(h, phase, part, a, st);
+        if (diag) return launch_group<NT, VAR_ALL, true>(h, phase, pt, a, st);
+        return launch_group<NT, VAR_ALL, false>(h, phase, pt, a, st);
     }
+    if (diag) return launch_group<NT, VAR_ONE, true>(h, phase, pt, a, st);
+    return launch_group<NT, VAR_ONE, false>(h, phase, pt, a, st);
 }
 
-static void run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, int part, cudaStream_t st)
+static int run_phase_all(mom5adv_ctx *h, const SwebyCall &c, int phase, const Part &pt, cudaStream_t st, bool diag_ok = true)
 {
-    for (int n0 = 0; n0 < c.ntr;) {
+    int rc = 0;
+    for (int n0 = 0; n0 < c.ntr && !rc;) {
         const int left = c.ntr - n0;
         // groups of <= MAXNT tracers; prefer an even split (e.g. 10 = 4 + 3 + 3) over 4 + 4 + 2
         const int ngroups = (left + MAXNT - 1) / MAXNT;
         const int nt = (left + ngroups - 1) / ngroups;
         switch (nt) {
-        case 1: run_phase<1>(h, c, n0, phase, part, st); break;
-        case 2: run_phase<2>(h, c, n0, phase, part, st); break;
-        case 3: run_phase<3>(h, c, n0, phase, part, st); break;
-        default: run_phase<4>(h, c, n0, phase, part, st); break;
+        case 1: rc = run_phase<1>(h, c, n0, phase, pt, diag_ok, st); break;
+        case 2: rc = run_phase<2>(h, c, n0, phase, pt, diag_ok, st); break;
+        case 3: rc = run_phase<3>(h, c, n0, phase, pt, diag_ok, st); break;
+        default: rc = run_phase<4>(h, c, n0, phase, pt, diag_ok, st); break;
         }
         n0 += nt;
     }
+    return rc;
 }
 
 static int zero_rings(mom5adv_ctx *h, double *const *arrs, int n, cudaStream_t st)
@@ -704,9 +739,16 @@ static bool plan_has_remote(const mom5adv_ctx *h, int flags)
     return false;
 }
 
-static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
+static Part part_of(int first, int step, int count)
 {
-    if (c.ntr < 1 || c.ntr > h->ntr_max) { set_error("sweby: ntr=%d outside 1..%d", c.ntr, h->ntr_max); return MOM5ADV_EINVAL; }
+    Part p;
+    p.first = first; p.step = step; p.count = count;
+    return p;
+}
+
+// Three separate sweeps (z, x, y), the running tracer materialised between them as the reference does.
+static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
+{
     int rc;
     const Geom &g = h->g;
     // y-sweep chunking (rows per j-chunk): >= ~4 waves of threads, at most 32 rows
@@ -724,9 +766,10 @@ static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     const bool ovx = h->overlap && plan_has_remote(h, 1) && nxt >= 4;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && njc >= 4;
     cudaStream_t sc = h->s_comm;
+    const Part all;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     zero_rings(h, c.adv, c.ntr, st);
-    run_phase_all(h, c, 0, 0, st);
+    if ((rc = run_phase_all(h, c, PH_Z, all, st))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[1], st));
     if (ovx) {
         CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
@@ -734,13 +777,13 @@ static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
         CUDA_TRY(cudaEventRecord(h->ev[2], st));
-        run_phase_all(h, c, 1, 1, st);
+        if ((rc = run_phase_all(h, c, PH_X, part_of(1, 1, nxt - 2), st))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
-        run_phase_all(h, c, 1, 2, st);
+        if ((rc = run_phase_all(h, c, PH_X, part_of(0, nxt - 1, 2), st))) return rc;
     } else {
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[2], st));
-        run_phase_all(h, c, 1, 0, st);
+        if ((rc = run_phase_all(h, c, PH_X, all, st))) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->ev[3], st));
     if (ovy) {
@@ -749,18 +792,93 @@ static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
         if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[3], sc));
         CUDA_TRY(cudaEventRecord(h->ev[4], st));
-        run_phase_all(h, c, 2, 1, st);
+        if ((rc = run_phase_all(h, c, PH_Y, part_of(1, 1, njc - 2), st))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[3], 0));
-        run_phase_all(h, c, 2, 2, st);
+        if ((rc = run_phase_all(h, c, PH_Y, part_of(0, njc - 1, 2), st))) return rc;
     } else {
         if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[4], st));
-        run_phase_all(h, c, 2, 0, st);
+        if ((rc = run_phase_all(h, c, PH_Y, all, st))) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->ev[5], st));
     h->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// z sweep, then x and y in one pass (k_sweby_xy): the x-updated tracer exists in HBM only on the four edge rows whose
+// north/south halo images the fused pass reads back.
+//   stream st : z edge tiles | z interior tiles | x on rows 1,2,nj-1,nj | xy interior chunks | xy edge chunks
+//   stream sc :                E/W strip update --^                       N/S strip update ----^
+static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
+{
+    int rc;
+    const Geom &g = h->g;
+    const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
+    {   // rows per j-chunk: every chunk redoes the x arithmetic of 4 rows, so as long as >= ~4 waves of blocks remain
+        int rows = FROWS_MAX;
+        while (rows > 8 && (long long)g.nk * nxb * ((g.nj + rows - 1) / rows) < 148LL * FMINB * 4) rows /= 2;
+        h->f_rows = rows;
+    }
+    const int rows = h->f_rows, njc = (g.nj + rows - 1) / rows;
+    const int nzt = (g.ni + ZBX - 1) / ZBX;
+    // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
+    const int c_hi = std::min((g.nj - 2) / rows - 1, njc - 1);
+    const bool need_y = !h->plan[2].recvs.empty();
+    const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 4;
+    const bool ovy = h->overlap && plan_has_remote(h, 2) && c_hi >= 1;
+    cudaStream_t sc = h->s_comm;
+    const Part all;
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    zero_rings(h, c.adv, c.ntr, st);
+    if (ovx) {
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(0, nzt - 1, 2), st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[0], 0));
+        if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(1, 1, nzt - 2), st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
+    } else {
+        if ((rc = run_phase_all(h, c, PH_Z, all, st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    if (need_y) {
+        Part south, north;
+        south.row_first = 1; south.row_last = std::min(2, g.nj);
+        north.row_first = std::max(3, g.nj - 1); north.row_last = g.nj;
+        if ((rc = run_phase_all(h, c, PH_X, south, st, false))) return rc;
+        if ((rc = run_phase_all(h, c, PH_X, north, st, false))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    if (need_y && ovy) {
+        CUDA_TRY(cudaEventRecord(h->ev_sync[2], st));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[2], 0));
+        if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, sc))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[3], sc));
+        CUDA_TRY(cudaEventRecord(h->ev[4], st));
+        if ((rc = run_phase_all(h, c, PH_XY, part_of(1, 1, c_hi), st))) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[3], 0));
+        if ((rc = run_phase_all(h, c, PH_XY, part_of(0, 1, 1), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_XY, part_of(c_hi + 1, 1, njc - 1 - c_hi), st))) return rc;
+    } else {
+        if (need_y && (rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[4], st));
+        if ((rc = run_phase_all(h, c, PH_XY, all, st))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    h->ev_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int sweby_dev(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
+{
+    if (c.ntr < 1 || c.ntr > h->ntr_max) { set_error("sweby: ntr=%d outside 1..%d", c.ntr, h->ntr_max); return MOM5ADV_EINVAL; }
+    return h->fuse ? sweby_dev_fused(h, c, st) : sweby_dev_unfused(h, c, st);
 }
 
 extern "C" int mom5adv_sweby_all_dev(mom5adv_handle h, int ntr, double dtime, const double *const *T, double *const *th,

@@ -35,13 +35,16 @@ struct SwebyArgs {
     double *adv[NT];            // y: T_prog(n)%wrk1 / Tracer%wrk1
     double *flux[NT];           // optional diagnostics (data-domain layout) or nullptr
     double *dadv[NT];           // optional per-direction tendency diagnostics or nullptr
+    double *flux2[NT], *dadv2[NT];   // fused x+y pass: the y sweep's diagnostics (flux/dadv are then the x sweep's)
     const double *u, *v, *w, *rho;
     const uint8_t *nib;         // mask nibbles of this sweep's direction, data-domain layout
+    const uint8_t *nib2;        // fused x+y pass: the y nibbles (nib holds the x nibbles)
     const double *dat, *datr, *dxte, *dyte, *dxtn, *dytn;
     double dtime, sl;
     int kc;                     // z/x: levels per k-chunk;  y: rows per j-chunk
     int accumulate;             // y: th += adv
-    int tile_first, tile_step;  // x: x-tile = tile_first + blockIdx.x*tile_step; y: j-chunk likewise (interior / edge launches)
+    int tile_first, tile_step;  // z, x: i-tile = tile_first + blockIdx.x*tile_step; y: j-chunk likewise (interior / edge launches)
+    int row_first, row_last;    // x: rows row_first..row_last (whole sweep: 1..nj; the fused pass needs the edge rows only)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
     constexpr int NF = NT + 2;                           // T(kp2)[NT], w, rho of the next level
     __shared__ double sm[2][NF][ZBX];
     const int tx = threadIdx.x;
-    const int i = blockIdx.x * ZBX + tx + 1;
+    const int i = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + tx + 1;
     const int j = blockIdx.y + 1;
     if (i > g.ni) return;                                // staging is per thread: no collective operation follows
     const int ks = blockIdx.z * a.kc + 1;
@@ -272,8 +275,8 @@ __global__ void __launch_bounds__(32 * XWARPS, XMINB) k_sweby_x(const Geom g, co
     const int lane = threadIdx.x, wy = threadIdx.y;
     const int iw = (a.tile_first + (int)blockIdx.x * a.tile_step) * 31;   // first east-face index of this warp
     const int i = iw + lane;                             // east-face index 0..ni; lanes >= 1 also update cell i
-    const int j = blockIdx.y * XWARPS + wy + 1;
-    if (j > g.nj) return;                                // whole warp leaves together
+    const int j = a.row_first + blockIdx.y * XWARPS + wy;
+    if (j > a.row_last) return;                          // whole warp leaves together
     const bool face_ok = (i <= g.ni);
     const bool cell_ok = face_ok && (lane >= 1);
     const int ic = min(i, g.ni);                         // clamped index for the loads of idle lanes

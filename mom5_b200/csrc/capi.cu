@@ -118,7 +118,7 @@ struct mom5adv_ctx {
 #define YROWS_MAX 32
 #endif
 #ifndef FROWS_MAX
-#define FROWS_MAX 64
+#define FROWS_MAX 128
 #endif
 
 #define LAUNCH(h, kern, grid, block, smem, st, ...)  \

@@ -29,8 +29,13 @@
 #define FWARPS 4     // warps per block = consecutive 31-cell x tiles at the same k
 #endif
 #ifndef FMINB
-#define FMINB 3
+#define FMINB 3     // 168 registers: no spills; 4 blocks (128 registers, 224 KB of shared memory, no L1 left) measured 35% slower
 #endif
+#ifndef FUNROLL
+#define FUNROLL 1
+#endif
+constexpr int kFusedUnroll = FUNROLL;
+#define RROW 34      // ring row: 32 lanes (+1 for rho's east neighbour, +1 pad)
 
 template <int NT>
 struct FusedLayout {
@@ -41,7 +46,7 @@ struct FusedLayout {
     static constexpr int X_DXTE = NT;
     static constexpr int NY = NT + 5;                 // y-only fields: th[NT], v, w(k), w(k-1), dxtn, dytn
     static constexpr int Y_V = NT, Y_WK = NT + 1, Y_WM = NT + 2, Y_DXTN = NT + 3, Y_DYTN = NT + 4;
-    static constexpr int RING = 4 * NR * XROW, XS = 2 * NX * XROW, YS = 2 * NY * 32;
+    static constexpr int RING = 4 * NR * RROW, XS = 2 * NX * XROW, YS = 2 * NY * 32;
     static constexpr int PER_WARP = RING + XS + YS;
     static constexpr size_t BYTES = (size_t)PER_WARP * FWARPS * sizeof(double);
 };
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
     typedef FusedLayout<NT> LY;
     extern __shared__ double fsm[];
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-    double *const ring = fsm + (size_t)wy * LY::PER_WARP;   // [4][NR][XROW]
+    double *const ring = fsm + (size_t)wy * LY::PER_WARP;   // [4][NR][RROW]
     double *const xs = ring + LY::RING;                     // [2][NX][XROW]
     double *const ys = xs + LY::XS;                         // [2][NY][32]
     // linear block id, k fastest (2-D metrics and w(k-1) of concurrently resident blocks hit in L2)
@@ -81,19 +86,19 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
 
     // ---- staging ----
     auto stage_row = [&](int r) {     // operands of row r (0 <= r <= nj+1): ring slot r & 3, x-only slot r & 1
-        double *R = ring + (r & 3) * (LY::NR * XROW), *X = xs + (r & 1) * (LY::NX * XROW);
+        double *R = ring + (r & 3) * (LY::NR * RROW), *X = xs + (r & 1) * (LY::NX * XROW);
         const ofs_t ro = (ofs_t)r * nxd, q = q0 + ro, c2 = c0 + ro, rt = (ofs_t)r * tp;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
             cp_async8(&X[n * XROW + lane], a.tm_in[n] + tqa0 + rt);
             if (lane < 3) cp_async8(&X[n * XROW + 32 + lane], a.tm_in[n] + tqb0 + rt);
-            cp_async8(&R[n * XROW + lane], a.T[n] + q);
+            cp_async8(&R[n * RROW + lane], a.T[n] + q);
         }
-        cp_async8(&R[LY::R_U * XROW + lane], a.u + q);
-        cp_async8(&R[LY::R_RHO * XROW + lane], a.rho + qr0 + ro);
-        if (lane == 0) cp_async8(&R[LY::R_RHO * XROW + 32], a.rho + qrb0 + ro);
-        cp_async8(&R[LY::R_DYTE * XROW + lane], a.dyte + c2);
-        cp_async8(&R[LY::R_DATR * XROW + lane], a.datr + c2);
+        cp_async8(&R[LY::R_U * RROW + lane], a.u + q);
+        cp_async8(&R[LY::R_RHO * RROW + lane], a.rho + qr0 + ro);
+        if (lane == 0) cp_async8(&R[LY::R_RHO * RROW + 32], a.rho + qrb0 + ro);
+        cp_async8(&R[LY::R_DYTE * RROW + lane], a.dyte + c2);
+        cp_async8(&R[LY::R_DATR * RROW + lane], a.datr + c2);
         cp_async8(&X[LY::X_DXTE * XROW + lane], a.dxte + c2);
     };
     auto stage_face = [&](int jf) {   // y-only operands of north face / cell row jf (0 <= jf <= nj): slot jf & 1
@@ -127,6 +132,7 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
 #pragma unroll
     for (int n = 0; n < NT; n++) { L.t0[n] = 0.0; L.t1[n] = 0.0; L.Rm1[n] = 0.0; L.R0[n] = 0.0; L.fprev[n] = 0.0; }
 
+#pragma unroll kFusedUnroll
     for (int jf = jf0; jf <= je; jf++) {
         const int r = jf + 2;                                       // row produced by this iteration
         __syncwarp();                                               // everyone is done with the slots about to be refilled
@@ -145,13 +151,13 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
 
         // ---------------- x: produce tm(i, r, k) -> L.t2 ----------------
         if (row_x(r)) {
-            const double *R = ring + (r & 3) * (LY::NR * XROW), *X = xs + (r & 1) * (LY::NX * XROW);
+            const double *R = ring + (r & 3) * (LY::NR * RROW), *X = xs + (r & 1) * (LY::NX * XROW);
             F.nb = nbx;
-            F.dyte = R[LY::R_DYTE * XROW + lane];
+            F.dyte = R[LY::R_DYTE * RROW + lane];
             F.dxte = X[LY::X_DXTE * XROW + lane];
-            F.uu = R[LY::R_U * XROW + lane];
-            F.rho_i = R[LY::R_RHO * XROW + lane];
-            F.rho_e = R[LY::R_RHO * XROW + lane + 1];
+            F.uu = R[LY::R_U * RROW + lane];
+            F.rho_i = R[LY::R_RHO * RROW + lane];
+            F.rho_e = R[LY::R_RHO * RROW + lane + 1];
 #pragma unroll
             for (int n = 0; n < NT; n++) {
                 F.tm1[n] = X[n * XROW + lane]; F.t0[n] = X[n * XROW + lane + 1];
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
                 for (int n = 0; n < NT; n++) F.f[n] = Z.f[n];
             }
             C.m_i = nib_and(nbx, 2u); C.rho_i = F.rho_i; C.mf = F.mf;
-            C.datr = R[LY::R_DATR * XROW + lane];
+            C.datr = R[LY::R_DATR * RROW + lane];
             C.mfw = __shfl_up_sync(0xffffffffu, F.mf, 1);
             const bool own_row = DIAG && (r >= js) && (r <= je);    // diagnostics are written by the chunk that owns the row
             const ofs_t qd = q0 + (ofs_t)r * nxd;
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
             for (int n = 0; n < NT; n++) {
                 C.f[n] = F.f[n];
                 C.fw[n] = __shfl_up_sync(0xffffffffu, F.f[n], 1);
-                C.Tc[n] = R[n * XROW + lane];
+                C.Tc[n] = R[n * RROW + lane];
                 C.t0[n] = F.t0[n];
                 if (DIAG && own_row && face_ok && a.flux[n]) a.flux[n][qd] = F.f[n];
             }
@@ -196,22 +202,22 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
 
         if (jf >= js - 1) {
             // ---------------- y: north face jf and (when live) cell (i, jf, k) ----------------
-            const double *R = ring + (jf & 3) * (LY::NR * XROW), *R1 = ring + ((jf + 1) & 3) * (LY::NR * XROW);
+            const double *R = ring + (jf & 3) * (LY::NR * RROW), *R1 = ring + ((jf + 1) & 3) * (LY::NR * RROW);
             const double *Y = ys + (jf & 1) * (LY::NY * 32);
-            if (jf == js - 1) L.rho0 = R[LY::R_RHO * XROW + lane];
+            if (jf == js - 1) L.rho0 = R[LY::R_RHO * RROW + lane];
             L.nb = nby;
             L.live = (jf >= js);
             L.vv = Y[LY::Y_V * 32 + lane];
-            L.rho1 = R1[LY::R_RHO * XROW + lane];
+            L.rho1 = R1[LY::R_RHO * RROW + lane];
             L.dxtn = Y[LY::Y_DXTN * 32 + lane];
             L.dytn = Y[LY::Y_DYTN * 32 + lane];
-            L.datr = R[LY::R_DATR * XROW + lane];
+            L.datr = R[LY::R_DATR * RROW + lane];
             L.wk = Y[LY::Y_WK * 32 + lane];
             L.wkm1 = has_km1 ? Y[LY::Y_WM * 32 + lane] : 0.0;
-            L.dyte_w = R[LY::R_DYTE * XROW + lw]; L.u_w = R[LY::R_U * XROW + lw];
-            L.dyte_c = R[LY::R_DYTE * XROW + lane]; L.u_c = R[LY::R_U * XROW + lane];
+            L.dyte_w = R[LY::R_DYTE * RROW + lw]; L.u_w = R[LY::R_U * RROW + lw];
+            L.dyte_c = R[LY::R_DYTE * RROW + lane]; L.u_c = R[LY::R_U * RROW + lane];
 #pragma unroll
-            for (int n = 0; n < NT; n++) L.Tc[n] = R[n * XROW + lane];
+            for (int n = 0; n < NT; n++) L.Tc[n] = R[n * RROW + lane];
             if (y_level<NT, VAR, false>(L)) {
                 YLevel<NT> Z = L;
                 y_level_exact<NT, VAR>(&Z);

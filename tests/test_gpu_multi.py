@@ -96,7 +96,9 @@ def _check(tmp_path, case, over, px, py):
 
 @pytest.mark.parametrize("case,over,px,py", [
     ("mini_tripolar", {}, 2, 1), ("mini_tripolar", {}, 1, 2), ("mini_walls", {}, 2, 1), ("mini_torus", {}, 1, 2),
-    ("global_1deg", dict(ntr=5), 2, 1), ("global_1deg", dict(ntr=5), 1, 2)])
+    ("global_1deg", dict(ntr=5), 2, 1), ("global_1deg", dict(ntr=5), 1, 2),
+    # wide / tall enough for the comm-compute overlap branches of both drivers (>= 4 z tiles per rank; interior j-chunks)
+    ("global_1deg", dict(ni=1040, nj=80, nk=6, ntr=3), 2, 1), ("global_1deg", dict(ni=1040, nj=80, nk=6, ntr=3), 1, 2)])
 def test_two_gpus(tmp_path, case, over, px, py):
     _check(tmp_path, case, over, px, py)
 

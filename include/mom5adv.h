@@ -44,6 +44,8 @@ extern "C" {
 #define MOM5ADV_ADVECT_QUICKER 5
 #define MOM5ADV_ADVECT_MDFL_SWEBY 9
 #define MOM5ADV_ADVECT_DST_LINEAR 10
+#define MOM5ADV_ADVECT_MDFL_SWEBY_TEST 12
+#define MOM5ADV_ADVECT_DST_LINEAR_TEST 14
 
 typedef struct mom5adv_ctx *mom5adv_handle;
 typedef struct mom5adv_comm_s *mom5adv_comm; /* wraps an ncclComm_t; NULL = single rank */

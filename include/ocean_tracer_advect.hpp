@@ -23,7 +23,8 @@
 namespace mom5 {
 
 // scheme ids, ocean_parameters.F90:149-163
-enum : int { ADVECT_UPWIND = 1, ADVECT_QUICKER = 5, ADVECT_MDFL_SWEBY = 9, ADVECT_DST_LINEAR = 10 };
+enum : int { ADVECT_UPWIND = 1, ADVECT_QUICKER = 5, ADVECT_MDFL_SWEBY = 9, ADVECT_DST_LINEAR = 10,
+             ADVECT_MDFL_SWEBY_TEST = 12, ADVECT_DST_LINEAR_TEST = 14 };
 
 // ocean_time_type (ocean_types.F90:937-947): 1-based time-level indices into field(:,:,:,1:3)
 struct ocean_time_type {
@@ -106,7 +107,8 @@ public:
         const double *rho_tau = Thickness.rho_dzt + n3_ * (size_t)(Time.tau - 1);
         if (!nml_.advect_sweby_all) {                                              // OTA:1923-2075
             switch (Tracer.horz_advect_scheme) {
-            case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR: break;
+            case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR:
+            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: break;
             default: throw std::runtime_error("==>Error from ocean_tracer_advect_mod (horz_advect_tracer): chose invalid horz advection scheme");
             }
             check(mom5adv_horz(h_, Tracer.horz_advect_scheme, dtime, level(Tracer.field, Time.taum1), level(Tracer.field, Time.tau),
@@ -134,7 +136,8 @@ public:
         if (nml_.zero_tracer_advect_vert) return;                                  // OTA:2109
         if (nml_.advect_sweby_all) return;                                         // OTA:2114
         switch (Tracer.vert_advect_scheme) {
-        case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR: break;
+        case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR:
+            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: break;
         default: throw std::runtime_error("==>Error from ocean_tracer_advect_mod (vert_advect_tracer): invalid advection scheme chosen");
         }
         check(mom5adv_vert(h_, Tracer.vert_advect_scheme, level(Tracer.field, Time.taum1), level(Tracer.field, Time.tau),

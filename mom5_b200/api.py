@@ -26,8 +26,11 @@ ADVECT_UPWIND = 1            # ocean_parameters.F90:149-163
 ADVECT_QUICKER = 5
 ADVECT_MDFL_SWEBY = 9
 ADVECT_DST_LINEAR = 10
+ADVECT_MDFL_SWEBY_TEST = 12
+ADVECT_DST_LINEAR_TEST = 14
 SCHEME_IDS = {"upwind": ADVECT_UPWIND, "quicker": ADVECT_QUICKER, "mdfl_sweby": ADVECT_MDFL_SWEBY,
-              "dst_linear": ADVECT_DST_LINEAR}
+              "dst_linear": ADVECT_DST_LINEAR, "mdfl_sweby_test": ADVECT_MDFL_SWEBY_TEST,
+              "dst_linear_test": ADVECT_DST_LINEAR_TEST}
 
 
 def _is_torch(a) -> bool:

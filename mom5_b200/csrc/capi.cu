@@ -16,6 +16,7 @@
 #include "mom5adv_internal.cuh"
 #include "sweby_kernels.cuh"
 #include "sweby_fused.cuh"
+#include "sweby_test_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -92,6 +93,7 @@ struct mom5adv_ctx {
     uint8_t *nibz = 0, *nibx = 0, *niby = 0;   // per-direction neighbourhood nibbles, data-domain layout
     QuickW qw{};                       // quicker weights (device)
     std::vector<double *> tmA, tmB;    // h2 scratch per tracer
+    double *st_ms = 0;                 // mass_mdfl of advect_tracer_mdfl_sweby_test (h2 scratch, allocated on first use)
     // halo machinery
     HaloPlan plan[4];                  // indexed by flags (1 = X, 2 = Y, 3 = XY)
     HaloPlan plan1;                    // halo-1 full update of data-domain arrays (field(taup1), OM:1903-1911)
@@ -575,7 +577,7 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
 {
     if (!h) return 0;
     cudaDeviceSynchronize();
-    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w})
+    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms})
         if (p) cudaFree(p);
     for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
         if (p) cudaFree(p);
@@ -1089,6 +1091,38 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
                     fx ? fxs : nullptr, fy ? fys : nullptr, fz ? fzs : nullptr, nullptr, nullptr, nullptr, 1};
         return sweby_dev(h, c, st);
     }
+    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST:
+    case MOM5ADV_ADVECT_DST_LINEAR_TEST: {
+        if (!w || !rho) { set_error("mom5adv_horz_dev: sweby_test needs wrho_bt and rho_dzt"); return MOM5ADV_EINVAL; }
+        int rc;
+        if (!h->st_ms) {
+            CUDA_TRY(cudaMalloc(&h->st_ms, nh2(h) * sizeof(double)));
+            CUDA_TRY(cudaMemset(h->st_ms, 0, nh2(h) * sizeof(double)));   // wall halos stay 0, as tmA / tmB (OTA:3500-3502)
+        }
+        STArgs a{};
+        a.T = Tm1; a.u = u; a.v = v; a.w = w; a.rho = rho; a.mask = h->mask;
+        a.dat = h->dat; a.datr = h->datr; a.dyte = h->dyte; a.dxtn = h->dxtn;
+        a.tr = h->tmA[0]; a.tms = h->tmB[0]; a.ms = h->st_ms;
+        a.fx = fx; a.fy = fy; a.fz = fz; a.th = th; a.wrk1 = wrk1;
+        a.dtime = dtime; a.sl = (scheme == MOM5ADV_ADVECT_MDFL_SWEBY_TEST) ? 1.0 : 0.0;
+        if (!a.fx && (rc = mirror(h, 0, &a.fx))) return rc;    // the reference's module-level flux_x / flux_y work arrays
+        if (!a.fy && (rc = mirror(h, 1, &a.fy))) return rc;
+        CUDA_TRY(cudaMemsetAsync(a.fx, 0, n3(h) * sizeof(double), st));   // flux_x = flux_y = 0 (OTA:3503-3504)
+        CUDA_TRY(cudaMemsetAsync(a.fy, 0, n3(h) * sizeof(double), st));
+        double *wz[1] = {wrk1};
+        zero_rings(h, wz, 1, st);                                          // Tracer%wrk1 = 0 on the data domain (OTA:1925-1931)
+        double *f3[3] = {a.tr, a.tms, a.ms};
+        const int nbx = (g.ni + 127) / 128, nbx1 = (g.ni + 1 + 127) / 128;
+        LAUNCH(h, k_st_z, dim3(nbx, g.nj), 128, 0, st, g, a);
+        if ((rc = halo_update(h, f3, 3, 1, st))) return rc;                // XUPDATE of the three fields (OTA:3582-3584)
+        LAUNCH(h, k_st_xflux, dim3(nbx1, g.nj, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_st_xupd, dim3(nbx, g.nj, g.nk), 128, 0, st, g, a);
+        if ((rc = halo_update(h, f3, 3, 2, st))) return rc;                // YUPDATE (OTA:3651-3653)
+        LAUNCH(h, k_st_yflux, dim3(nbx, g.nj + 1, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_st_yupd, dim3(nbx, g.nj, g.nk), 128, 0, st, g, a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     case MOM5ADV_ADVECT_UPWIND: {
         double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
         int rc;
@@ -1128,7 +1162,9 @@ extern "C" int mom5adv_vert_dev(mom5adv_handle h, int scheme, const double *Tm1,
     cudaStream_t st = (cudaStream_t)stream;
     switch (scheme) {
     case MOM5ADV_ADVECT_MDFL_SWEBY:
-    case MOM5ADV_ADVECT_DST_LINEAR:   // three-dimensional schemes: wrk1 = 0, th unchanged (OTA:2116-2122, 2147-2155)
+    case MOM5ADV_ADVECT_DST_LINEAR:
+    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST:
+    case MOM5ADV_ADVECT_DST_LINEAR_TEST:   // three-dimensional schemes: wrk1 = 0, th unchanged (OTA:2116-2122, 2147-2155)
         CUDA_TRY(cudaMemsetAsync(wrk1, 0, n3(h) * sizeof(double), st));
         return 0;
     case MOM5ADV_ADVECT_UPWIND:

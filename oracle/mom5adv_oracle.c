@@ -349,6 +349,134 @@ void orc_sweby_all_y(const orc_block *b, int ntr, double dtime, const double *co
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * advect_tracer_mdfl_sweby_test (OTA:3469-3746): the mass-weighted variant.  Three running fields on the halo-2
+ * scratch: tracer_mdfl (tr), tracermass_mdfl (tms), mass_mdfl (ms); the CFL number is |massflux|*dtime/mass of
+ * the upwind cell; theta's denominator is sign(1e-30,Rj)+Rj (sign BIT of Rj, as IEEE processors do).
+ * ---------------------------------------------------------------------------------------------- */
+static inline double test_flux(double Rjp, double Rj, double Rjm, double massflux, double cfl, double Tup, double Tdn,
+                               double mA, double mB, double sl)
+{
+    double d0 = ((2.0 - cfl) * (1.0 - cfl)) * ONESIXTH;
+    double d1 = (1.0 - (cfl * cfl)) * ONESIXTH;
+    double den = copysign(1.0e-30, Rj) + Rj;
+    double thetaP = Rjm / den;
+    double thetaM = Rjp / den;
+    double psiP = d0 + (d1 * thetaP);
+    psiP = (psiP * (1.0 - sl)) +
+           (orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaP)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaP)) * sl);
+    double psiM = d0 + (d1 * thetaM);
+    psiM = (psiM * (1.0 - sl)) +
+           (orc_max(0.0, orc_min(orc_min(1.0, d0 + (d1 * thetaM)), ((1.0 - cfl) / (1.0e-30 + cfl)) * thetaM)) * sl);
+    return ((0.5 * (((massflux + fabs(massflux)) * (Tup + (psiP * Rj))) + ((massflux - fabs(massflux)) * (Tdn - (psiM * Rj))))) * mA) * mB;
+}
+
+/* OTA:3505-3580.  tr/tms/ms: h2 scratch, zeroed here (OTA:3500-3502); flux_z optional. */
+void orc_sweby_test_z(const orc_block *b, double dtime, double sl, const double *T, const double *w, const double *rho,
+                      double *tr, double *tms, double *ms, double *flux_z)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    const size_t nh = (size_t)NX2(b) * NY2(b) * nk;
+    double *ftp = (double *)calloc((size_t)ni * nj, sizeof(double));
+    double *wkm1 = (double *)calloc((size_t)ni * nj, sizeof(double));
+    memset(tr, 0, sizeof(double) * nh);
+    memset(tms, 0, sizeof(double) * nh);
+    memset(ms, 0, sizeof(double) * nh);
+    for (int k = 1; k <= nk; k++) {
+        int kp1 = imin(k + 1, nk), kp2 = imin(k + 2, nk), km1 = imax(k - 1, 1);
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t c = (size_t)(i - 1) + (size_t)ni * (j - 1), h = H3(b, i, j, k);
+                double Tk = T[D3(b, i, j, k)], Tkp1 = T[D3(b, i, j, kp1)];
+                double dat = b->dat[D2(b, i, j)];
+                tr[h] = Tk;
+                ms[h] = rho[D3(b, i, j, k)] * dat;
+                tms[h] = ms[h] * Tk;
+                double Rjp = ((T[D3(b, i, j, km1)] - Tk) * m[H3(b, i, j, km1)]) * m[H3(b, i, j, k)];
+                double Rj = ((Tk - Tkp1) * m[H3(b, i, j, k)]) * m[H3(b, i, j, kp1)];
+                double Rjm = ((Tkp1 - T[D3(b, i, j, kp2)]) * m[H3(b, i, j, kp1)]) * m[H3(b, i, j, kp2)];
+                double wk = w[W3(b, i, j, k)];
+                double massflux = dat * wk, cfl;
+                if (massflux * rho[D3(b, i, j, kp1)] > 0.0) cfl = (fabs(wk) * dtime) / rho[D3(b, i, j, kp1)];
+                else if (massflux * rho[D3(b, i, j, k)] < 0.0) cfl = (fabs(wk) * dtime) / rho[D3(b, i, j, k)];
+                else cfl = 0.0;
+                double fbt = test_flux(Rjp, Rj, Rjm, massflux, cfl, Tkp1, Tk, m[H3(b, i, j, kp1)], m[H3(b, i, j, k)], sl);
+                ms[h] = ms[h] + ((dtime * dat) * (wk - wkm1[c]));
+                tms[h] = tms[h] + (dtime * (fbt - ftp[c]));
+                if (ms[h] > 0.) tr[h] = tms[h] / ms[h];
+                if (flux_z) flux_z[D3(b, i, j, k)] = fbt;
+                ftp[c] = fbt;
+                wkm1[c] = wk;
+            }
+    }
+    free(ftp);
+    free(wkm1);
+}
+
+/* OTA:3585-3649.  flux_x: data-domain array, zeroed by the caller (OTA:3503), faces i = 0..ni written. */
+void orc_sweby_test_x(const orc_block *b, double dtime, double sl, const double *u, double *tr, double *tms, double *ms,
+                      double *flux_x)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 1; j <= nj; j++)
+            for (int i = 0; i <= ni; i++) {
+                double t0 = tr[H3(b, i, j, k)], t1 = tr[H3(b, i + 1, j, k)];
+                double Rjp = ((tr[H3(b, i + 2, j, k)] - t1) * m[H3(b, i + 2, j, k)]) * m[H3(b, i + 1, j, k)];
+                double Rj = ((t1 - t0) * m[H3(b, i + 1, j, k)]) * m[H3(b, i, j, k)];
+                double Rjm = ((t0 - tr[H3(b, i - 1, j, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i - 1, j, k)];
+                double massflux = b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)], cfl;
+                if (massflux * ms[H3(b, i, j, k)] > 0.0) cfl = (fabs(massflux) * dtime) / ms[H3(b, i, j, k)];
+                else if (massflux * ms[H3(b, i + 1, j, k)] < 0.0) cfl = (fabs(massflux) * dtime) / ms[H3(b, i + 1, j, k)];
+                else cfl = 0.0;
+                flux_x[D3(b, i, j, k)] = test_flux(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i + 1, j, k)], sl);
+            }
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t h = H3(b, i, j, k);
+                ms[h] = ms[h] + (dtime * ((b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)]) - (b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)])));
+                tms[h] = tms[h] + (dtime * (flux_x[D3(b, i - 1, j, k)] - flux_x[D3(b, i, j, k)]));
+                if (ms[h] > 0.) tr[h] = tms[h] / ms[h];
+            }
+    }
+}
+
+/* OTA:3655-3736.  wrk1_out = Tracer%wrk1 on the compute domain: the caller's negation (OTA:1970-1975) applied. */
+void orc_sweby_test_y(const orc_block *b, double dtime, double sl, const double *T, const double *v, const double *rho,
+                      double *tr, double *tms, double *ms, double *flux_y, double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const double *m = b->tmask_h2;
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 0; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                double t0 = tr[H3(b, i, j, k)], t1 = tr[H3(b, i, j + 1, k)];
+                double Rjp = ((tr[H3(b, i, j + 2, k)] - t1) * m[H3(b, i, j + 2, k)]) * m[H3(b, i, j + 1, k)];
+                double Rj = ((t1 - t0) * m[H3(b, i, j + 1, k)]) * m[H3(b, i, j, k)];
+                double Rjm = ((t0 - tr[H3(b, i, j - 1, k)]) * m[H3(b, i, j, k)]) * m[H3(b, i, j - 1, k)];
+                double massflux = b->dxtn[D2(b, i, j)] * v[D3(b, i, j, k)], cfl;
+                if (massflux * ms[H3(b, i, j, k)] > 0.0) cfl = (fabs(massflux) * dtime) / ms[H3(b, i, j, k)];
+                else if (massflux * ms[H3(b, i, j + 1, k)] < 0.0) cfl = (fabs(massflux) * dtime) / ms[H3(b, i, j + 1, k)];
+                else cfl = 0.0;
+                flux_y[D3(b, i, j, k)] = test_flux(Rjp, Rj, Rjm, massflux, cfl, t0, t1, m[H3(b, i, j, k)], m[H3(b, i, j + 1, k)], sl);
+            }
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t h = H3(b, i, j, k);
+                ms[h] = ms[h] + (dtime * ((b->dxtn[D2(b, i, j - 1)] * v[D3(b, i, j - 1, k)]) - (b->dxtn[D2(b, i, j)] * v[D3(b, i, j, k)])));
+                tms[h] = tms[h] + (dtime * (flux_y[D3(b, i, j - 1, k)] - flux_y[D3(b, i, j, k)]));
+                if (ms[h] > 0.) tr[h] = tms[h] / ms[h];
+            }
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                double f = (m[H3(b, i, j, k)] * ((rho[D3(b, i, j, k)] * T[D3(b, i, j, k)]) - (tms[H3(b, i, j, k)] * b->datr[D2(b, i, j)]))) / dtime;
+                wrk1_out[D3(b, i, j, k)] = -f;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * advect_tracer_mdfl_sweby (OTA:3806-4066)
  * ---------------------------------------------------------------------------------------------- */
 void orc_mdfl_sweby_z(const orc_block *b, double dtime, double sl, const double *T, const double *w,

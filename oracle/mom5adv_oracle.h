@@ -8,6 +8,7 @@
  * It restates, operation for operation, the arithmetic of
  *   /root/reference/src/mom5/ocean_tracers/ocean_tracer_advect.F90   ("OTA")
  * for advect_tracer_sweby_all (OTA:4104-4511), advect_tracer_mdfl_sweby (OTA:3806-4066),
+ * advect_tracer_mdfl_sweby_test (OTA:3469-3746),
  * horz/vert_advect_tracer_quicker (OTA:2538-2653, 2981-3031) + quicker_init (OTA:1442-1586),
  * horz/vert_advect_tracer_upwind (OTA:2238-2294, 2792-2824), and the FMS halo-update
  * semantics they rely on (src/shared/mpp/include/mpp_do_update.h:57-78,
@@ -101,6 +102,15 @@ void orc_mdfl_sweby_y(const orc_block *b, double dtime, double sweby_limiter,
                       const double *T, const double *uhrho_et, const double *vhrho_nt,
                       const double *wrho_bt, const double *rho_dzt,
                       double *tm, double *flux_y, double *wrk1_out);
+
+/* ---- advect_tracer_mdfl_sweby_test (OTA:3469-3746), one tracer; tr/tms/ms = tracer_mdfl, tracermass_mdfl, mass_mdfl
+ *      (h2 scratch; XUPDATE of all three between z and x, YUPDATE between x and y) ---- */
+void orc_sweby_test_z(const orc_block *b, double dtime, double sweby_limiter, const double *T, const double *wrho_bt,
+                      const double *rho_dzt, double *tr, double *tms, double *ms, double *flux_z);
+void orc_sweby_test_x(const orc_block *b, double dtime, double sweby_limiter, const double *uhrho_et,
+                      double *tr, double *tms, double *ms, double *flux_x);
+void orc_sweby_test_y(const orc_block *b, double dtime, double sweby_limiter, const double *T, const double *vhrho_nt,
+                      const double *rho_dzt, double *tr, double *tms, double *ms, double *flux_y, double *wrk1_out);
 
 /* ---- quicker (OTA:1442-1586, 2538-2653, 2981-3031) ---- */
 void orc_quicker_init_pre(const orc_block *b);    /* fills tmask_h2/dxt_h2/dyt_h2 before their halo updates  */

@@ -245,6 +245,29 @@ class Oracle:
                                     _ptr(self.w[ib]), _ptr(self.rho[ib]), _ptr(tm[ib]), _ptr(fy[ib]), _ptr(wrk1[ib]))
         return dict(wrk1=wrk1, flux_x=fx, flux_y=fy, flux_z=fz, tm=tm)
 
+    def sweby_test(self, T: List[np.ndarray], dtime: float, sweby_limiter: float = 1.0):
+        """advect_tracer_mdfl_sweby_test (OTA:3469-3746) behind the dispatcher arm OTA:1970-1975"""
+        if not self._mdfl_ready:
+            self.mdfl_init()
+        T = [_np(t) for t in T]
+        tr = [b.h2() for b in self.blocks]; tms = [b.h2() for b in self.blocks]; ms = [b.h2() for b in self.blocks]
+        fx = [b.d1() for b in self.blocks]; fy = [b.d1() for b in self.blocks]; fz = [b.d1() for b in self.blocks]
+        wrk1 = [b.d1() for b in self.blocks]
+        dt, sl = C.c_double(dtime), C.c_double(sweby_limiter)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_sweby_test_z(C.byref(b.c), dt, sl, _ptr(T[ib]), _ptr(self.w[ib]), _ptr(self.rho[ib]),
+                                    _ptr(tr[ib]), _ptr(tms[ib]), _ptr(ms[ib]), _ptr(fz[ib]))
+        for f in (tr, tms, ms):
+            self.update(f, 2, XUPDATE)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_sweby_test_x(C.byref(b.c), dt, sl, _ptr(self.u[ib]), _ptr(tr[ib]), _ptr(tms[ib]), _ptr(ms[ib]), _ptr(fx[ib]))
+        for f in (tr, tms, ms):
+            self.update(f, 2, YUPDATE)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_sweby_test_y(C.byref(b.c), dt, sl, _ptr(T[ib]), _ptr(self.v[ib]), _ptr(self.rho[ib]),
+                                    _ptr(tr[ib]), _ptr(tms[ib]), _ptr(ms[ib]), _ptr(fy[ib]), _ptr(wrk1[ib]))
+        return dict(wrk1=wrk1, flux_x=fx, flux_y=fy, flux_z=fz, tracer=tr, tracermass=tms, mass=ms)
+
     # ---- quicker ----
     def horz_quicker(self, Tm1, Tt, tmask_limit, limit_with_upwind: bool):
         if not self._quick_ready:

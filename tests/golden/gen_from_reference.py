@@ -14,7 +14,8 @@ Routines executed from the reference text (line ranges located by their `subrout
     mdfl_init (mask part) .......... tmask_mdfl
     quicker_init (weights part) .... quick_*, curv_*, dxt_quick, tmask_quick
     advect_tracer_sweby_all ........ th_tendency, T_prog%wrk1, all registered diagnostics
-    horz_advect_tracer ............. dispatcher arms upwind / quicker / mdfl_sweby / dst_linear
+    advect_tracer_mdfl_sweby_test .. mass-weighted variant (tracer, tracer mass and cell mass carried through the sweeps)
+    horz_advect_tracer ............. dispatcher arms upwind / quicker / mdfl_sweby / dst_linear / *_test
     vert_advect_tracer ............. dispatcher arms upwind / quicker
 What is NOT reference text: the halo filler standing in for FMS mpp_update_domains (single domain: cyclic
 wrap, folded north edge, walls untouched; CGRID_NE fold fix) -- that restates
@@ -23,6 +24,7 @@ known-answer pattern (test_mpp_domains.F90:5628-5634, 3749-3766) in tests/test_h
 """
 from __future__ import annotations
 
+import math
 import os
 import re
 import sys
@@ -121,6 +123,7 @@ def build_env(gen, b, src):
     isd, ied, jsd, jed = 0, ni + 1, 0, nj + 1
     dec = s.decomposition(1, 1)
     env = dict(FArray=FArray, S=S, nint=nint, min=min, max=max, abs=abs,
+               sign=lambda a, b: math.copysign(abs(a), b),   # IEEE processors: the sign BIT of b (also for b = -0.0)
                isc=isc, iec=iec, jsc=jsc, jec=jec, isd=isd, ied=ied, jsd=jsd, jed=jed, nk=nk,
                num_prog_tracers=ntr, XUPDATE=XUPDATE, YUPDATE=YUPDATE, CGRID_NE=2, FATAL=2,
                onesixth=1.0 / 6.0, have_obc=False, async_domain_update=False, limit_with_upwind=False,
@@ -157,7 +160,7 @@ def build_env(gen, b, src):
     h2 = lambda: FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2), (1, nk)])
     for nm in ("flux_x", "flux_y", "flux_z", "wrk1", "advect_tendency", "neutral_temp_advect", "neutral_salt_advect"):
         env[nm] = d1()
-    for nm in ("tmask_mdfl", "tracer_mdfl", "tmask_quick", "tracer_quick"):
+    for nm in ("tmask_mdfl", "tracer_mdfl", "mass_mdfl", "tracermass_mdfl", "tmask_quick", "tracer_quick"):
         env[nm] = h2()
     env["tracer_mdfl_all"] = FList([Obj(field=h2()) for _ in range(ntr)])
     env["dxt_quick"] = FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2)])
@@ -229,6 +232,7 @@ def run_case(name):
 
     cites = {}
     for kind, nm in (("subroutine", "advect_tracer_sweby_all"), ("function", "advect_tracer_mdfl_sweby"),
+                     ("function", "advect_tracer_mdfl_sweby_test"),
                      ("function", "horz_advect_tracer_upwind"), ("function", "vert_advect_tracer_upwind"),
                      ("function", "horz_advect_tracer_quicker"), ("function", "vert_advect_tracer_quicker"),
                      ("subroutine", "horz_advect_tracer"), ("subroutine", "vert_advect_tracer")):
@@ -278,12 +282,13 @@ def run_case(name):
         out[f"quicker_init.{nm}"] = env[nm].a.copy()
 
     arms = [("upwind", "ADVECT_UPWIND", False), ("quicker", "ADVECT_QUICKER", False), ("quicker_lim", "ADVECT_QUICKER", True),
-            ("mdfl_sweby", "ADVECT_MDFL_SWEBY", False), ("dst_linear", "ADVECT_DST_LINEAR", False)]
+            ("mdfl_sweby", "ADVECT_MDFL_SWEBY", False), ("dst_linear", "ADVECT_DST_LINEAR", False),
+            ("mdfl_sweby_test", "ADVECT_MDFL_SWEBY_TEST", False), ("dst_linear_test", "ADVECT_DST_LINEAR_TEST", False)]
     for tag, scheme, lim in arms:
         t0 = time.time()
         reset()
         env["limit_with_upwind"] = lim
-        n = 1 if tag != "quicker_lim" else min(2, ntr)
+        n = min(2, ntr) if tag in ("quicker_lim", "dst_linear_test") else 1
         tr = T_prog(n)
         tr.horz_advect_scheme = tr.vert_advect_scheme = env[scheme]
         env["horz_advect_tracer"](env["Time"], env["Adv_vel"], env["Thickness"], env["Dens"], T_prog, tr, n, s.dtime)
@@ -291,6 +296,9 @@ def run_case(name):
         out[f"{tag}.horz.th_tendency"] = tr.th_tendency.a.copy()
         out[f"{tag}.flux_x"] = env["flux_x"].a.copy()
         out[f"{tag}.flux_y"] = env["flux_y"].a.copy()
+        if tag.endswith("_test"):   # the three running fields after the y sweep (compute domain is what matters)
+            for nm in ("tracer_mdfl", "tracermass_mdfl", "mass_mdfl"):
+                out[f"{tag}.{nm}"] = env[nm].a.copy()
         env["vert_advect_tracer"](env["Time"], env["Adv_vel"], env["Dens"], env["Thickness"], T_prog, tr, n, s.dtime)
         out[f"{tag}.vert.wrk1"] = tr.wrk1.a.copy()
         out[f"{tag}.vert.th_tendency"] = tr.th_tendency.a.copy()

@@ -69,7 +69,7 @@ def test_sweby_all_host_pointer_mode(name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("tag", ["mdfl_sweby", "dst_linear", "quicker", "quicker_lim", "upwind"])
+@pytest.mark.parametrize("tag", ["mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test", "quicker", "quicker_lim", "upwind"])
 def test_dispatcher_arms_vs_reference_golden(name, tag):
     from mom5_b200.api import SCHEME_IDS, TracerAdvect
     b, gold, _ = load_golden(name)
@@ -93,6 +93,36 @@ def test_dispatcher_arms_vs_reference_golden(name, tag):
     assert_bit_equal(wrk1, gold[f"{tag}.vert.wrk1"], "vert wrk1")
     assert_bit_equal(th, gold[f"{tag}.vert.th_tendency"], "th after vert")
     assert_bit_equal(fz[:, 1:-1, 1:-1], gold[f"{tag}.flux_z"][:, 1:-1, 1:-1], "flux_z")
+    adv.close()
+
+
+@pytest.mark.parametrize("case,over", [("mini_tripolar", {}), ("mini_torus", {}), ("global_1deg", dict(ni=130, nj=70, nk=50, ntr=2, cfl=0.9)),
+                                       ("gyre", dict(ni=96, nj=80, nk=20, ntr=2))])
+@pytest.mark.parametrize("tag,sl", [("mdfl_sweby_test", 1.0), ("dst_linear_test", 0.0)])
+def test_sweby_test_variant_vs_oracle(case, over, tag, sl, sweep_mode):
+    """advect_tracer_mdfl_sweby_test (OTA:3469-3746) on larger seeded cases: wrk1, th_tendency and the three fluxes"""
+    from mom5_b200.api import SCHEME_IDS, TracerAdvect
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    if sweep_mode == "unfused":
+        pytest.skip("not a Sweby-driver test")
+    g = make_case(case, **over)
+    b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    ref = o.sweby_test([b.T[0].numpy()], g.s.dtime, sl)
+    adv = TracerAdvect(b, ntracers_max=1)
+    th = torch.zeros_like(_dev(b.T[0]))
+    wrk1 = torch.full_like(th, -777.0)
+    fx, fy, fz = torch.full_like(th, 5.0), torch.full_like(th, 5.0), torch.zeros_like(th)
+    adv.horz_advect_tracer(SCHEME_IDS[tag], _dev(b.T[0]), th, wrk1, _dev(b.uhrho_et), _dev(b.vhrho_nt), g.s.dtime,
+                           wrho_bt=_dev(b.wrho_bt), rho_dzt=_dev(b.rho_dzt), flux_x=fx, flux_y=fy, flux_z=fz)
+    torch.cuda.synchronize()
+    assert_bit_equal(wrk1, ref["wrk1"][0], f"{case} {tag} wrk1")
+    assert_bit_equal(th[:, 1:-1, 1:-1], (0.0 + ref["wrk1"][0])[:, 1:-1, 1:-1], f"{case} {tag} th (0 + wrk1: -0 becomes +0)")
+    assert_bit_equal(fx, ref["flux_x"][0], "flux_x")
+    assert_bit_equal(fy, ref["flux_y"][0], "flux_y")
+    assert_bit_equal(fz[:, 1:-1, 1:-1], ref["flux_z"][0][:, 1:-1, 1:-1], "flux_z")
+    assert float(wrk1.abs().max()) > 0
     adv.close()
 
 

@@ -73,6 +73,28 @@ def test_mdfl_sweby(name, tag, sl):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("tag,sl", [("mdfl_sweby_test", 1.0), ("dst_linear_test", 0.0)])
+def test_mdfl_sweby_test_variant(name, tag, sl):
+    """advect_tracer_mdfl_sweby_test (OTA:3469-3746): mass-weighted CFL, sign(1e-30,Rj), three running fields"""
+    import ctypes as C
+    from oracle.oracle import _ptr
+    b, gold, _ = load_golden(name)
+    _, o = _oracle(b)
+    n = int(gold[f"{tag}.tracer"])
+    out = o.sweby_test([b.T[n - 1].numpy()], b.spec.dtime, sl)
+    assert_bit_equal(out["wrk1"][0], gold[f"{tag}.horz.wrk1"], "wrk1")
+    th = b.th_tendency[n - 1].numpy().copy()
+    o.L.orc_accumulate(C.byref(o.blocks[0].c), _ptr(out["wrk1"][0]), _ptr(th))
+    assert_bit_equal(th, gold[f"{tag}.horz.th_tendency"], "th_tendency")
+    assert_bit_equal(out["flux_x"][0], gold[f"{tag}.flux_x"], "flux_x")
+    assert_bit_equal(out["flux_y"][0], gold[f"{tag}.flux_y"], "flux_y")
+    assert_bit_equal(out["flux_z"][0][:, 1:-1, 1:-1], gold[f"{tag}.flux_z"][:, 1:-1, 1:-1], "flux_z")
+    for nm, key in (("tracer", "tracer_mdfl"), ("tracermass", "tracermass_mdfl"), ("mass", "mass_mdfl")):
+        assert_bit_equal(out[nm][0][:, 2:-2, 2:-2], gold[f"{tag}.{key}"][:, 2:-2, 2:-2], key)
+    assert not gold[f"{tag}.vert.wrk1"].any()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_quicker_init(name):
     b, gold, _ = load_golden(name)
     _, o = _oracle(b)

@@ -381,7 +381,8 @@ def run_e2e(args, adv, spec, b, T, th, out, u, v, w, rho, world, rank, dev, cell
     h2d = (2 * ntr + 3) * n3 * 8 + nw * 8
     d2h = 2 * ntr * n3 * 8
     return dict(value=cells * ntr / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3,
-                steps=steps, api="mom5adv_sweby_all (host pointers, pinned)", pcie_gbs=(h2d + d2h) / dt / 1e9)
+                steps=steps, api="mom5adv_sweby_all (host pointers, pinned; copy pipeline over "
+                          + ("j-bands" if os.environ.get("MOM5ADV_BANDED", "1") != "0" and os.environ.get("MOM5ADV_FUSE", "1") != "0" else "tracers") + ")", pcie_gbs=(h2d + d2h) / dt / 1e9)
 
 
 def main():

@@ -111,6 +111,7 @@ struct mom5adv_ctx {
     int fuse = 1;                      // MOM5ADV_FUSE=0: three separate sweeps instead of z + fused x/y
     int f_rows = 64;
     std::vector<cudaEvent_t> ev_up, ev_done;
+    int banded = 1;                    // MOM5ADV_BANDED=0: host-pointer sweby_all pipelines over tracers instead of j-bands
     cudaEvent_t ev[6];
     bool ev_valid = false;
     int64_t launches = 0;
@@ -541,6 +542,7 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sync[e], cudaEventDisableTiming));
     if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
     if (const char *fu = getenv("MOM5ADV_FUSE")) h->fuse = atoi(fu);
+    if (const char *bd = getenv("MOM5ADV_BANDED")) h->banded = atoi(bd);
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
     h->ev_up.resize(ntracers_max); h->ev_done.resize(ntracers_max);
     for (int n = 0; n < ntracers_max; n++) {
@@ -628,7 +630,9 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
     if (phase == PH_Z) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
         const int nzt = (g.ni + ZBX - 1) / ZBX;
-        dim3 grid(pt.count < 0 ? nzt : pt.count, g.nj, (g.nk + b.kc - 1) / b.kc);
+        const int nrows = b.row_last - b.row_first + 1;
+        if (nrows <= 0) return 0;
+        dim3 grid(pt.count < 0 ? nzt : pt.count, nrows, (g.nk + b.kc - 1) / b.kc);
         LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, ZBX, 0, st, g, b);
     } else if (phase == PH_X) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
@@ -808,6 +812,15 @@ static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st
     return 0;
 }
 
+static void pick_f_rows(mom5adv_ctx *h)
+{   // rows per j-chunk of the fused pass: every chunk redoes the x arithmetic of 4 rows, so as large as >= ~4 waves of blocks allow
+    const Geom &g = h->g;
+    const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
+    int rows = FROWS_MAX;
+    while (rows > 8 && (long long)g.nk * nxb * ((g.nj + rows - 1) / rows) < 148LL * FMINB * 4) rows /= 2;
+    h->f_rows = rows;
+}
+
 // z sweep, then x and y in one pass (k_sweby_xy): the x-updated tracer exists in HBM only on the four edge rows whose
 // north/south halo images the fused pass reads back.
 //   stream st : z edge tiles | z interior tiles | x on rows 1,2,nj-1,nj | xy interior chunks | xy edge chunks
@@ -816,12 +829,7 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
     int rc;
     const Geom &g = h->g;
-    const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
-    {   // rows per j-chunk: every chunk redoes the x arithmetic of 4 rows, so as long as >= ~4 waves of blocks remain
-        int rows = FROWS_MAX;
-        while (rows > 8 && (long long)g.nk * nxb * ((g.nj + rows - 1) / rows) < 148LL * FMINB * 4) rows /= 2;
-        h->f_rows = rows;
-    }
+    pick_f_rows(h);
     const int rows = h->f_rows, njc = (g.nj + rows - 1) / rows;
     const int nzt = (g.ni + ZBX - 1) / ZBX;
     // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
@@ -915,6 +923,95 @@ static int mirror_w(mom5adv_ctx *h, double **out)
 #define H2D(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyHostToDevice, st))
 #define D2H(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyDeviceToHost, st))
 
+// Host-pointer sweby_all as a pipeline over j-BANDS (one band = one j-chunk of the fused pass): while band b is on its way
+// up the PCIe link, the SMs run the z sweep of band b-1 and the fused x/y pass of the chunk below it, and the results of
+// finished chunks travel down -- both copy engines stay busy for the whole call instead of idling during the upload of
+// the velocity fields (tracer-wise pipeline) and the download of the last tracer.  Single-rank layouts only: the E/W
+// strip update (cyclic wrap) is redone after every band, which across ranks would need matching band counts.
+//   chunk c (rows c*R+1 .. (c+1)*R) reads the z-updated tracer on rows <= (c+1)*R + 2  ->  it runs after band c+1;
+//   chunks touching a halo row of the x-updated tracer (the first, the last one or two) run at the end, after the edge-row
+//   x sweep and the N/S strip update, exactly as in sweby_dev_fused.
+static int band_copy(const Geom &g, double *dst, const double *src, int ja, int jb, int nlev, cudaMemcpyKind kind, cudaStream_t st)
+{
+    const size_t pitch = (size_t)g.slab * sizeof(double), ofs = (size_t)ja * g.nxd;
+    CUDA_TRY(cudaMemcpy2DAsync(dst + ofs, pitch, src + ofs, pitch, (size_t)(jb - ja + 1) * g.nxd * sizeof(double), (size_t)nlev, kind, st));
+    return 0;
+}
+
+static int sweby_all_banded(mom5adv_ctx *h, int ntr, double dtime, const double *const *T, double *const *th, double *const *adv,
+                            const double *u, const double *v, const double *w, const double *rho, double *du, double *dv,
+                            double *dw, double *dr, double *const *dT, double *const *dth, double *const *dadv)
+{
+    const Geom &g = h->g;
+    int rc;
+    pick_f_rows(h);
+    const int R = h->f_rows, njc = (g.nj + R - 1) / R;
+    const int c_hi = std::min((g.nj - 2) / R - 1, njc - 1);
+    cudaStream_t st = h->stream, up = h->s_up, down = h->s_down;
+    while ((int)h->ev_up.size() < njc + 1) {
+        cudaEvent_t e1, e2;
+        CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        h->ev_up.push_back(e1); h->ev_done.push_back(e2);
+    }
+    std::vector<const double *> cT(dT, dT + ntr);
+    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, cT.data(), dth, dadv, du, dv, dw, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1};
+    zero_rings(h, dadv, ntr, st);
+    auto download = [&](int ja, int jb, int evi) -> int {          // rows ja..jb of th, adv once the compute stream got here
+        CUDA_TRY(cudaEventRecord(h->ev_done[evi], st));
+        CUDA_TRY(cudaStreamWaitEvent(down, h->ev_done[evi], 0));
+        for (int n = 0; n < ntr; n++) {
+            if ((rc = band_copy(g, th[n], dth[n], ja, jb, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
+            if (adv && adv[n] && (rc = band_copy(g, adv[n], dadv[n], ja, jb, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
+        }
+        return 0;
+    };
+    for (int b = 0; b < njc; b++) {
+        const int ja = (b == 0) ? 0 : b * R + 1, jb = (b == njc - 1) ? g.nj + 1 : (b + 1) * R;
+        const cudaMemcpyKind H = cudaMemcpyHostToDevice;
+        if ((rc = band_copy(g, du, u, ja, jb, g.nk, H, up)) || (rc = band_copy(g, dv, v, ja, jb, g.nk, H, up)) ||
+            (rc = band_copy(g, dr, rho, ja, jb, g.nk, H, up)) || (rc = band_copy(g, dw, w, ja, jb, g.nk + 1, H, up))) return rc;
+        for (int n = 0; n < ntr; n++)
+            if ((rc = band_copy(g, dT[n], T[n], ja, jb, g.nk, H, up)) || (rc = band_copy(g, dth[n], th[n], ja, jb, g.nk, H, up))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_up[b], up));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_up[b], 0));
+        Part zp;
+        zp.row_first = std::max(ja, 1); zp.row_last = std::min(jb, g.nj);
+        if ((rc = run_phase_all(h, c, PH_Z, zp, st))) return rc;
+        if ((rc = halo_update(h, h->tmA.data(), ntr, 1, st))) return rc;   // E/W strips (all rows; rows of later bands are redone)
+        const int ch = b - 1;                                             // the chunk that has just become computable
+        if (ch >= 1 && ch <= c_hi) {
+            if ((rc = run_phase_all(h, c, PH_XY, part_of(ch, 1, 1), st))) return rc;
+            if ((rc = download(ch * R + 1, (ch + 1) * R, b))) return rc;
+        }
+    }
+    // edge chunks: x sweep on the four edge rows, N/S strip update of the x-updated tracer, then the chunks that read it
+    if (!h->plan[2].recvs.empty()) {
+        Part south, north;
+        south.row_first = 1; south.row_last = std::min(2, g.nj);
+        north.row_first = std::max(3, g.nj - 1); north.row_last = g.nj;
+        if ((rc = run_phase_all(h, c, PH_X, south, st, false)) || (rc = run_phase_all(h, c, PH_X, north, st, false))) return rc;
+        if ((rc = halo_update(h, h->tmB.data(), ntr, 2, st))) return rc;
+    }
+    const int first_tail = std::max(c_hi + 1, 1);
+    if ((rc = run_phase_all(h, c, PH_XY, part_of(0, 1, 1), st))) return rc;
+    if (njc > first_tail && (rc = run_phase_all(h, c, PH_XY, part_of(first_tail, 1, njc - first_tail), st))) return rc;
+    if (njc > 1) {
+        if ((rc = download(0, R, njc))) return rc;                         // chunk 0 with the south halo row
+        // remaining rows up to the north halo row, in one go
+        CUDA_TRY(cudaStreamWaitEvent(down, h->ev_done[njc], 0));
+        for (int n = 0; n < ntr; n++) {
+            if ((rc = band_copy(g, th[n], dth[n], first_tail * R + 1, g.nj + 1, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
+            if (adv && adv[n] && (rc = band_copy(g, adv[n], dadv[n], first_tail * R + 1, g.nj + 1, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
+        }
+    } else if ((rc = download(0, g.nj + 1, njc))) return rc;
+    h->ev_valid = false;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(down));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const double *const *T, double *const *th,
                                  double *const *adv, const double *u, const double *v, const double *w, const double *rho,
                                  double *const *fx, double *const *fy, double *const *fz, double *const *ax, double *const *ay,
@@ -948,6 +1045,10 @@ extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const 
         }
     bool any_diag = false;
     for (int q = 0; q < 6; q++) any_diag |= (hd[q] != nullptr);
+    pick_f_rows(h);
+    if (!any_diag && h->banded && h->fuse && !plan_has_remote(h, 1) && !plan_has_remote(h, 2) &&
+        (h->g.nj + h->f_rows - 1) / h->f_rows >= 4)
+        return sweby_all_banded(h, ntr, dtime, T, th, adv, u, v, w, rho, du, dv, dw, dr, dT.data(), dth.data(), dadv.data());
     if (!any_diag && ntr > 1) {
         // Pipelined over tracers: the copy engines run in both directions while the SMs work on another tracer.
         //   up stream  : u, v, w, rho, then (T_n, th_n) for n = 0, 1, ...

@@ -44,7 +44,8 @@ struct SwebyArgs {
     int kc;                     // z/x: levels per k-chunk;  y: rows per j-chunk
     int accumulate;             // y: th += adv
     int tile_first, tile_step;  // z, x: i-tile = tile_first + blockIdx.x*tile_step; y: j-chunk likewise (interior / edge launches)
-    int row_first, row_last;    // x: rows row_first..row_last (whole sweep: 1..nj; the fused pass needs the edge rows only)
+    int row_first, row_last;    // z, x: rows row_first..row_last (whole sweep: 1..nj; the fused pass needs x on the edge rows only,
+                                // the banded host-pointer pipeline runs z band by band)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
     __shared__ double sm[2][NF][ZBX];
     const int tx = threadIdx.x;
     const int i = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + tx + 1;
-    const int j = blockIdx.y + 1;
+    const int j = a.row_first + (int)blockIdx.y;
     if (i > g.ni) return;                                // staging is per thread: no collective operation follows
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);

@@ -114,11 +114,16 @@ __device__ __forceinline__ unsigned z_level(ZLevel<NT> &L)
 template <int NT, int VAR>
 __device__ __noinline__ void z_level_exact(ZLevel<NT> *L) { z_level<NT, VAR, true>(*L); }
 
+#ifndef ZSTAGES
+#define ZSTAGES 2    // staging depth: operands of level k + ZSTAGES - 1 are in flight while level k is computed
+#endif
+
 template <int NT, int VAR, bool DIAG>
 __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const SwebyArgs<NT> a)
 {
-    constexpr int NF = NT + 2;                           // T(kp2)[NT], w, rho of the next level
-    __shared__ double sm[2][NF][ZBX];
+    constexpr int NF = NT + 2;                           // T(kp2)[NT], w, rho of a level
+    constexpr int D = ZSTAGES;
+    __shared__ double sm[D][NF][ZBX];
     const int tx = threadIdx.x;
     const int i = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + tx + 1;
     const int j = a.row_first + (int)blockIdx.y;
@@ -134,21 +139,37 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
 
     ofs_t qd = (ofs_t)d3(g, i, j, k0);                            // data-domain offset of level k
     ofs_t qt = (ofs_t)t3(g, i, j, k0);                            // h2 offset of level k
-    ofs_t q2 = qd + slab * (ofs_t)(min(k0 + 2, g.nk) - k0);       // data-domain offset of level min(k+2, nk)
     const ofs_t qkm = (k0 > 1) ? qd - slab : qd, qkp = (k0 < g.nk) ? qd + slab : qd;
 
-    auto stage = [&](int st, ofs_t qd_, ofs_t q2_) {   // operands of the level whose offsets are (qd_, q2_)
+    // staging front: level kf, its data-domain offset qf and the offset q2f of level min(kf+2, nk)
+    int kf = k0;
+    ofs_t qf = qd, q2f = qd + slab * (ofs_t)(min(k0 + 2, g.nk) - k0);
+    auto stage_next = [&](int slot) -> unsigned {                 // stages T(min(kf+2,nk)), w(kf), rho(kf); returns the nibble of kf
+        unsigned nb = 0;
+        if (kf <= ke) {
 #pragma unroll
-        for (int n = 0; n < NT; n++) cp_async8(&sm[st][n][tx], a.T[n] + q2_);
-        cp_async8(&sm[st][NT][tx], a.w + qd_ + slab);             // w3(k) = d3(k) + slab
-        cp_async8(&sm[st][NT + 1][tx], a.rho + qd_);
+            for (int n = 0; n < NT; n++) cp_async8(&sm[slot][n][tx], a.T[n] + q2f);
+            cp_async8(&sm[slot][NT][tx], a.w + qf + slab);        // w3(k) = d3(k) + slab
+            cp_async8(&sm[slot][NT + 1][tx], a.rho + qf);
+            nb = a.nib[qf];
+        }
+        qf += slab;
+        if (kf + 3 <= g.nk) q2f += slab;
+        kf++;
+        return nb;
     };
-    stage(0, qd, q2);
-    cp_async_commit();
+    unsigned nbq[D - 1];                                          // mask nibbles of levels k+1 .. k+D-1
+    unsigned nb_first = 0;
+#pragma unroll
+    for (int d = 0; d < D - 1; d++) {
+        const unsigned nb = stage_next(d);
+        if (d == 0) nb_first = nb; else nbq[d - 1] = nb;
+        cp_async_commit();
+    }
 
     ZLevel<NT> L;
     L.dat = a.dat[c2]; L.datr = a.datr[c2]; L.dtime = a.dtime; L.sl = a.sl;
-    L.nb = a.nib[qd];
+    L.nb = nb_first;
 #pragma unroll
     for (int n = 0; n < NT; n++) {
         const double Tkm = a.T[n][qkm];
@@ -160,19 +181,13 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
     }
     L.wkm1 = 0.0;
 
-    int st = 0;
+    int st = 0, sf = D - 1;                                       // slot consumed / slot filled this iteration
 #pragma unroll 3
-    for (int k = k0; k <= ke; k++, st ^= 1) {
-        // ---- stage the operands of level k+1 (each thread reads back only what it staged itself) ----
-        const ofs_t qd_n = qd + slab;
-        const ofs_t q2_n = (k + 3 <= g.nk) ? q2 + slab : q2;
-        unsigned nb_n = 0;
-        if (k < ke) {
-            stage(st ^ 1, qd_n, q2_n);
-            nb_n = a.nib[qd_n];
-        }
+    for (int k = k0; k <= ke; k++) {
+        // ---- stage the operands of level k+D-1 (each thread reads back only what it staged itself) ----
+        nbq[D - 2] = stage_next(sf);
         cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<D - 1>();
 #pragma unroll
         for (int n = 0; n < NT; n++) L.Tp2[n] = sm[st][n][tx];
         L.wk = sm[st][NT][tx];
@@ -199,10 +214,13 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
             L.Tp1[n] = L.Tp2[n];
         }
         L.wkm1 = L.wk;
-        L.nb = nb_n;
-        qd = qd_n;
-        q2 = q2_n;
+        L.nb = nbq[0];
+#pragma unroll
+        for (int d = 0; d + 1 < D - 1; d++) nbq[d] = nbq[d + 1];
+        qd += slab;
         qt += (ofs_t)g.tslab;
+        st = (st + 1 == D) ? 0 : st + 1;
+        sf = (sf + 1 == D) ? 0 : sf + 1;
     }
 }
 

@@ -138,6 +138,16 @@ int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const dou
                               const double *rho_dztr_taup1, const double *const *T_taum1,
                               const double *const *th_tendency, double *const *T_taup1, void *stream);
 
+/* The same consumer FUSED onto the advection pass: update_advection_only (ocean_tracer.F90:2618-2649) with
+ * advect_tracer_sweby_all as the operator.  th_tendency := 0 + T_prog(n)%wrk1 and
+ * T_taup1[n] := (rho_dzt_taum1*T_taum1[n] + dtime*th_tendency)*rho_dztr_taup1 are formed in the epilogue of the x/y pass,
+ * followed by the halo-1 update of T_taup1[n].  th_out / adv_out (arrays of ntr pointers, or NULL, or NULL entries) receive
+ * th_tendency / wrk1 on the compute domain when wanted; leaving them NULL saves their HBM traffic.                     */
+int mom5adv_sweby_all_step_dev(mom5adv_handle h, int ntr, double dtime, const double *const *T_taum1,
+                               const double *rho_dzt_taum1, const double *rho_dztr_taup1,
+                               const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt, const double *rho_dzt_tau,
+                               double *const *T_taup1, double *const *th_out, double *const *adv_out, void *stream);
+
 /* ---- producer of wrho_bt ----------------------------------------------------------
  * diverge_t(:,:,k) = tmask*(BDX_ET(uhrho_et) + BDY_NT(vhrho_nt)) and the continuity recurrence
  * wrho_bt(:,:,k) = ((rho_dzt_tendency - mass_source) + diverge_t(:,:,k) + wrho_bt(:,:,k-1))*tmask over the whole data
@@ -146,6 +156,22 @@ int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const dou
 int mom5adv_continuity_dev(mom5adv_handle h, const double *uhrho_et, const double *vhrho_nt,
                            const double *rho_dzt_tendency, const double *mass_source, double *wrho_bt,
                            double *diverge_t, void *stream);
+
+/* ---- diagnostics producers ------------------------------------------------------
+ * mom5adv_adv_diss_dev: compute_adv_diss (OTA:7547-7712), called from vert_advect_tracer's tail (OTA:2221-2223): the
+ * tracer's own horizontal and vertical advection operators applied to field(tau)**2, then
+ * adv_diss = -(conversion**2)/dtime * (adv*(2*rho_dzt(tau)*T + dtime*adv) - rho_dzt(taup1)*t2_tendency) on the compute
+ * domain, 0 elsewhere.  advect_tendency = horz + vert Tracer%wrk1 (OTA:2000-2006, 2170-2176).  t2_tendency (the
+ * reference's wrk1, diagnostic id_tracer2_advection before its conversion**2 factor) may be NULL.  Schemes as mom5adv_horz /
+ * mom5adv_vert; ADVECT_MDFL_SWEBY_TEST has no arm in the reference's select, its horizontal operator is 0.
+ * mom5adv_flux_int_z_dev: the z-integrated flux diagnostics *_xflux_adv_int_z / *_yflux_adv_int_z (OTA:4317-4326,
+ * 4449-4458): out2d(i,j) = sum over k (in order) of flux3d(i,j,k) on the compute domain, 0 elsewhere.              */
+int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_scheme, double dtime, double conversion,
+                         const double *T_tau, const double *tmask_limit, int limit_with_upwind,
+                         const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
+                         const double *rho_dzt_tau, const double *rho_dzt_taup1, const double *advect_tendency,
+                         double *adv_diss, double *t2_tendency, void *stream);
+int mom5adv_flux_int_z_dev(mom5adv_handle h, const double *flux3d, double *out2d, void *stream);
 
 /* ---- metrics on device arrays ---------------------------------------------------------------------------
  * mom5adv_chksum_dev: mpp_chksum of the compute domain (wrap-around sum of the int64 bit patterns,

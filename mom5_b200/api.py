@@ -168,10 +168,31 @@ class TracerAdvect:
         check(self.L.mom5adv_tracer_update_dev(self.handle, len(T_taum1), float(dtime), _ptr(rho_dzt_taum1), _ptr(rho_dztr_taup1),
                                                _pp(T_taum1), _pp(th_tendency), _pp(T_taup1), _cur_stream()), "tracer_update_dev")
 
+    # ---- update_advection_only with sweby_all as the operator, time update fused into the x/y pass ----
+    def advect_sweby_all_and_update(self, T_taum1: Sequence, T_taup1: Sequence, rho_dzt_taum1, rho_dztr_taup1, uhrho_et, vhrho_nt,
+                                    wrho_bt, rho_dzt_tau, dtime: float, th_tendency: Optional[Sequence] = None,
+                                    adv_tendency: Optional[Sequence] = None):
+        check(self.L.mom5adv_sweby_all_step_dev(self.handle, len(T_taum1), float(dtime), _pp(T_taum1), _ptr(rho_dzt_taum1),
+                                                _ptr(rho_dztr_taup1), _ptr(uhrho_et), _ptr(vhrho_nt), _ptr(wrho_bt), _ptr(rho_dzt_tau),
+                                                _pp(T_taup1), _pp(th_tendency) if th_tendency is not None else None,
+                                                _pp(adv_tendency) if adv_tendency is not None else None, _cur_stream()),
+              "sweby_all_step_dev")
+
     # ---- continuity: wrho_bt from the horizontal transports (ocean_advection_velocity.F90:660-669) ----
     def continuity(self, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tendency=None, mass_source=None, diverge_t=None):
         check(self.L.mom5adv_continuity_dev(self.handle, _ptr(uhrho_et), _ptr(vhrho_nt), _ptr(rho_dzt_tendency), _ptr(mass_source),
                                             _ptr(wrho_bt), _ptr(diverge_t), _cur_stream()), "continuity_dev")
+
+    # ---- diagnostics producers: compute_adv_diss (OTA:7547-7712), z-integrated fluxes (OTA:4317-4326) ----
+    def adv_diss(self, horz_scheme: int, vert_scheme: int, T_tau, advect_tendency, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tau,
+                 rho_dzt_taup1, dtime: float, adv_diss_out, conversion: float = 1.0, tmask_limit=None, t2_tendency=None):
+        check(self.L.mom5adv_adv_diss_dev(self.handle, int(horz_scheme), int(vert_scheme), float(dtime), float(conversion),
+                                          _ptr(T_tau), _ptr(tmask_limit), int(self.limit_with_upwind), _ptr(uhrho_et), _ptr(vhrho_nt),
+                                          _ptr(wrho_bt), _ptr(rho_dzt_tau), _ptr(rho_dzt_taup1), _ptr(advect_tendency),
+                                          _ptr(adv_diss_out), _ptr(t2_tendency), _cur_stream()), "adv_diss_dev")
+
+    def flux_int_z(self, flux3d, out2d):
+        check(self.L.mom5adv_flux_int_z_dev(self.handle, _ptr(flux3d), _ptr(out2d), _cur_stream()), "flux_int_z_dev")
 
     # ---- metrics ----
     def chksum(self, field, masked: bool = False) -> int:

@@ -651,13 +651,23 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
         const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
         b.kc = h->f_rows;
         const int njc = (g.nj + b.kc - 1) / b.kc;
+        const unsigned nblk = (unsigned)(g.nk * nxb * (pt.count < 0 ? njc : pt.count));
+        if (VAR == VAR_ALL && !DIAG && b.Tnew[0]) {   // time update in the epilogue (mom5adv_sweby_all_step_dev)
+            typedef FusedLayout<NT, true> LYU;
+            static bool attr_upd = false;
+            if (!attr_upd) {
+                CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR_ALL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LYU::BYTES));
+                attr_upd = true;
+            }
+            LAUNCH(h, (k_sweby_xy<NT, VAR_ALL, false, true>), nblk, 32 * FWARPS, LYU::BYTES, st, g, b, nxb, nxt);
+            return 0;
+        }
         static bool attr_set = false;   // per instantiation
         if (!attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedLayout<NT>::BYTES));
             attr_set = true;
         }
-        LAUNCH(h, (k_sweby_xy<NT, VAR, DIAG>), (unsigned)(g.nk * nxb * (pt.count < 0 ? njc : pt.count)), 32 * FWARPS,
-               FusedLayout<NT>::BYTES, st, g, b, nxb, nxt);
+        LAUNCH(h, (k_sweby_xy<NT, VAR, DIAG>), nblk, 32 * FWARPS, FusedLayout<NT>::BYTES, st, g, b, nxb, nxt);
     }
     return 0;
 }
@@ -670,6 +680,9 @@ struct SwebyCall {
     const double *u, *v, *w, *rho;
     double *const *fx, *const *fy, *const *fz, *const *ax, *const *ay, *const *az;
     int accumulate;
+    // time update fused into the x/y pass (mom5adv_sweby_all_step_dev); th / adv entries may then be null
+    double *const *Tnew = nullptr;
+    const double *rho_m1 = nullptr, *rho_r = nullptr;
 };
 
 // diag_ok = false: never write diagnostics from this launch (edge-row x sweep ahead of the fused pass, which writes them)
@@ -685,7 +698,8 @@ static int run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cons
         if (phase == PH_Z) { a.tm_in[n] = h->tmA[n0 + n]; }
         if (phase == PH_X || phase == PH_XY) { a.tm_in[n] = h->tmA[n0 + n]; a.tm_out[n] = h->tmB[n0 + n]; }
         if (phase == PH_Y) { a.tm_in[n] = h->tmB[n0 + n]; }
-        if (phase == PH_Y || phase == PH_XY) { a.th[n] = c.th ? c.th[n0 + n] : nullptr; a.adv[n] = c.adv[n0 + n]; }
+        if (phase == PH_Y || phase == PH_XY) { a.th[n] = c.th ? c.th[n0 + n] : nullptr; a.adv[n] = c.adv ? c.adv[n0 + n] : nullptr; }
+        if (phase == PH_XY && c.Tnew) a.Tnew[n] = c.Tnew[n0 + n];
         if (diag_ok) {
             a.flux[n] = fl ? fl[n0 + n] : nullptr;
             a.dadv[n] = da ? da[n0 + n] : nullptr;
@@ -701,6 +715,7 @@ static int run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cons
     a.nib2 = h->niby;
     a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
     a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;
+    a.rho_m1 = c.rho_m1; a.rho_r = c.rho_r;
     if (c.var == VAR_ALL) {
         if (diag) return launch_group<NT, VAR_ALL, true>(h, phase, pt, a, st);
         return launch_group<NT, VAR_ALL, false>(h, phase, pt, a, st);
@@ -840,7 +855,7 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     cudaStream_t sc = h->s_comm;
     const Part all;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
-    zero_rings(h, c.adv, c.ntr, st);
+    if (c.adv) zero_rings(h, c.adv, c.ntr, st);
     if (ovx) {
         if ((rc = run_phase_all(h, c, PH_Z, part_of(0, nzt - 1, 2), st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
@@ -1334,6 +1349,62 @@ extern "C" int mom5adv_vert(mom5adv_handle h, int scheme, const double *Tm1, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// diagnostics producers
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_scheme, double dtime, double conversion,
+                                    const double *T_tau, const double *tlimit, int limit_with_upwind, const double *u,
+                                    const double *v, const double *w, const double *rho_tau, const double *rho_taup1,
+                                    const double *advect_tendency, double *adv_diss, double *t2_tendency, void *stream)
+{
+    if (!h || !T_tau || !u || !v || !w || !rho_tau || !rho_taup1 || !advect_tendency || !adv_diss) {
+        set_error("mom5adv_adv_diss_dev: null argument");
+        return MOM5ADV_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geom &g = h->g;
+    const size_t N = n3(h);
+    int rc;
+    double *sq, *w2, *w3, *thd;   // wrk1 (squared tracer), wrk2, wrk3 of the reference; thd absorbs the dispatchers' th += wrk1
+    if ((rc = mirror(h, 2, &sq)) || (rc = mirror(h, 3, &w2)) || (rc = mirror(h, 4, &w3)) || (rc = mirror(h, 5, &thd))) return rc;
+    CUDA_TRY(cudaMemsetAsync(thd, 0, N * sizeof(double), st));
+    LAUNCH(h, k_square, 148 * 8, 256, 0, st, N, T_tau, sq);
+    switch (horz_scheme) {   // OTA:7583-7626: the operator acts on the squared tracer at BOTH time levels
+    case MOM5ADV_ADVECT_UPWIND: case MOM5ADV_ADVECT_QUICKER: case MOM5ADV_ADVECT_MDFL_SWEBY: case MOM5ADV_ADVECT_DST_LINEAR:
+    case MOM5ADV_ADVECT_DST_LINEAR_TEST:
+        if ((rc = mom5adv_horz_dev(h, horz_scheme, dtime, sq, sq, tlimit, limit_with_upwind, u, v, w, rho_tau, thd, w2, nullptr, nullptr, nullptr, st))) return rc;
+        break;
+    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST:   // has no arm in compute_adv_diss's select: wrk2 stays 0
+        CUDA_TRY(cudaMemsetAsync(w2, 0, N * sizeof(double), st));
+        break;
+    default:
+        set_error("mom5adv_adv_diss_dev: horz advection scheme %d is not covered by the GPU path", horz_scheme);
+        return MOM5ADV_EINVAL;
+    }
+    switch (vert_scheme) {   // OTA:7628-7662
+    case MOM5ADV_ADVECT_UPWIND: case MOM5ADV_ADVECT_QUICKER: case MOM5ADV_ADVECT_MDFL_SWEBY: case MOM5ADV_ADVECT_DST_LINEAR:
+    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST: case MOM5ADV_ADVECT_DST_LINEAR_TEST:
+        if ((rc = mom5adv_vert_dev(h, vert_scheme, sq, sq, tlimit, w, thd, w3, nullptr, st))) return rc;
+        break;
+    default:
+        set_error("mom5adv_adv_diss_dev: vert advection scheme %d is not covered by the GPU path", vert_scheme);
+        return MOM5ADV_EINVAL;
+    }
+    DissArgs a{rho_tau, rho_taup1, T_tau, advect_tendency, w2, w3, t2_tendency, adv_diss, dtime, 1.0 / dtime, conversion};
+    LAUNCH(h, k_adv_diss, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mom5adv_flux_int_z_dev(mom5adv_handle h, const double *flux3d, double *out2d, void *stream)
+{
+    if (!h || !flux3d || !out2d) { set_error("mom5adv_flux_int_z_dev: null argument"); return MOM5ADV_EINVAL; }
+    const Geom &g = h->g;
+    LAUNCH(h, k_flux_int_z, dim3((g.ni + 2 + 127) / 128, g.nj + 2), 128, 0, (cudaStream_t)stream, g, flux3d, out2d);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // consumer of the tendencies: tracer time update + halo-1 update (ocean_tracer.F90:2341-2350, ocean_model.F90:1903-1911)
 // ------------------------------------------------------------------------------------------------
 extern "C" int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime, const double *rho_dzt_taum1,
@@ -1352,6 +1423,30 @@ extern "C" int mom5adv_tracer_update_dev(mom5adv_handle h, int ntr, double dtime
         a.rho_m1 = rho_dzt_taum1; a.rho_r = rho_dztr_taup1; a.dtime = dtime;
         LAUNCH(h, k_tracer_update<MAXNT>, dim3((g.ni + 127) / 128, g.nj, g.nk), 128, 0, st, g, a);
     }
+    std::vector<double *> f(T_taup1, T_taup1 + ntr);
+    return halo_update_l<1>(h, f.data(), ntr, 3, st);
+}
+
+// update_advection_only (ocean_tracer.F90:2618-2649) with advect_tracer_sweby_all as the advection operator, in two
+// kernels per tracer group: z sweep, then the fused x/y pass whose epilogue forms th_tendency = 0 + wrk1 and
+// field(taup1) = (rho_dzt(taum1)*field(taum1) + dtime*th_tendency)*rho_dztr; then the halo-1 update of field(taup1)
+// (ocean_model.F90:1903-1911).  Saves, per cell and tracer, the read of th_tendency, the writes of th_tendency and wrk1 (when
+// the caller passes NULL for them) and the whole stand-alone update pass.
+extern "C" int mom5adv_sweby_all_step_dev(mom5adv_handle h, int ntr, double dtime, const double *const *T_taum1,
+                                          const double *rho_dzt_taum1, const double *rho_dztr_taup1, const double *u, const double *v,
+                                          const double *w, const double *rho_tau, double *const *T_taup1, double *const *th_out,
+                                          double *const *adv_out, void *stream)
+{
+    if (!h || !T_taum1 || !rho_dzt_taum1 || !rho_dztr_taup1 || !u || !v || !w || !rho_tau || !T_taup1) {
+        set_error("mom5adv_sweby_all_step_dev: null argument");
+        return MOM5ADV_EINVAL;
+    }
+    if (!h->fuse) { set_error("mom5adv_sweby_all_step_dev needs the fused driver (MOM5ADV_FUSE=0 is set)"); return MOM5ADV_EUNSUP; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, T_taum1, th_out, adv_out, u, v, w, rho_tau, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    c.Tnew = T_taup1; c.rho_m1 = rho_dzt_taum1; c.rho_r = rho_dztr_taup1;
+    int rc = sweby_dev(h, c, st);
+    if (rc) return rc;
     std::vector<double *> f(T_taup1, T_taup1 + ntr);
     return halo_update_l<1>(h, f.data(), ntr, 3, st);
 }

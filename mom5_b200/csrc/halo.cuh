@@ -83,6 +83,47 @@ __global__ void __launch_bounds__(128) k_tracer_update(const Geom g, const UpdAr
         if (a.Tnew[n]) a.Tnew[n][q] = ((r0 * a.T[n][q]) + (a.dtime * a.th[n][q])) * rr;
 }
 
+// compute_adv_diss (OTA:7547-7712), element-wise parts: wrk1 = field(tau)**2 over the data domain (OTA:7574-7580) ...
+__global__ void k_square(const size_t n, const double *__restrict__ T, double *__restrict__ out)
+{
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = T[q] * T[q];
+}
+// ... and wrk1 = wrk2 + wrk3, wrk4 = -(conversion**2)*dtimer*(term1 + term2) on the compute domain, 0 elsewhere (OTA:7680-7701)
+struct DissArgs {
+    const double *rho_tau, *rho_taup1, *T_tau, *adv, *wrk2, *wrk3;
+    double *t2, *diss;
+    double dtime, dtimer, conversion;
+};
+__global__ void __launch_bounds__(128) k_adv_diss(const Geom g, const DissArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // 0..ni+1
+    const int j = blockIdx.y, k = blockIdx.z + 1;                // 0..nj+1
+    if (i > g.ni + 1) return;
+    const size_t q = d3(g, i, j, k);
+    double w1 = 0.0, d = 0.0;
+    if (i >= 1 && i <= g.ni && j >= 1 && j <= g.nj) {
+        w1 = a.wrk2[q] + a.wrk3[q];
+        const double at = a.adv[q];
+        const double term1 = at * (((2.0 * a.rho_tau[q]) * a.T_tau[q]) + (a.dtime * at));
+        const double term2 = -(a.rho_taup1[q] * w1);
+        d = (-(a.conversion * a.conversion) * a.dtimer) * (term1 + term2);
+    }
+    if (a.t2) a.t2[q] = w1;
+    a.diss[q] = d;
+}
+
+// z-integrated flux diagnostics (OTA:4317-4326, 4449-4458): out(i,j) = sum_k flux(i,j,k) in k order, compute domain, 0 elsewhere
+__global__ void __launch_bounds__(128) k_flux_int_z(const Geom g, const double *__restrict__ flux, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i > g.ni + 1) return;
+    double acc = 0.0;
+    if (i >= 1 && i <= g.ni && j >= 1 && j <= g.nj)
+        for (int k = 1; k <= g.nk; k++) acc = acc + flux[d3(g, i, j, k)];
+    out[d2(g, i, j)] = acc;
+}
+
 // compute-domain copy between a data-domain array and an h2 field (tracer_quick / tmask staging)
 __global__ void k_d1_to_h2(const Geom g, const double *__restrict__ src, double *__restrict__ dst)
 {

@@ -37,24 +37,27 @@
 constexpr int kFusedUnroll = FUNROLL;
 #define RROW 34      // ring row: 32 lanes (+1 for rho's east neighbour, +1 pad)
 
-template <int NT>
+// UPD: the epilogue also performs update_advection_only's time update (ocean_tracer.F90:2618-2649):
+//   th_tendency = 0 + T_prog%wrk1;  field(taup1) = (rho_dzt(taum1)*field(taum1) + dtime*th_tendency)*rho_dztr
+// th_tendency is then not read, and neither it nor wrk1 has to be written (null pointers skip the stores).
+template <int NT, bool UPD = false>
 struct FusedLayout {
     // per-warp shared memory, in doubles
     static constexpr int NR = NT + 4;                 // ring fields: T[NT], u, rho, dyte, datr
     static constexpr int R_U = NT, R_RHO = NT + 1, R_DYTE = NT + 2, R_DATR = NT + 3;
     static constexpr int NX = NT + 1;                 // x-only fields: tm(z)[NT], dxte
     static constexpr int X_DXTE = NT;
-    static constexpr int NY = NT + 5;                 // y-only fields: th[NT], v, w(k), w(k-1), dxtn, dytn
-    static constexpr int Y_V = NT, Y_WK = NT + 1, Y_WM = NT + 2, Y_DXTN = NT + 3, Y_DYTN = NT + 4;
+    static constexpr int NY = NT + 5 + (UPD ? 2 : 0); // y-only fields: th[NT], v, w(k), w(k-1), dxtn, dytn (+ rho_dzt(taum1), rho_dztr)
+    static constexpr int Y_V = NT, Y_WK = NT + 1, Y_WM = NT + 2, Y_DXTN = NT + 3, Y_DYTN = NT + 4, Y_RM1 = NT + 5, Y_RR = NT + 6;
     static constexpr int RING = 4 * NR * RROW, XS = 2 * NX * XROW, YS = 2 * NY * 32;
     static constexpr int PER_WARP = RING + XS + YS;
     static constexpr size_t BYTES = (size_t)PER_WARP * FWARPS * sizeof(double);
 };
 
-template <int NT, int VAR, bool DIAG>
+template <int NT, int VAR, bool DIAG, bool UPD = false>
 __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, const SwebyArgs<NT> a, const int nxb, const int nxt)
 {
-    typedef FusedLayout<NT> LY;
+    typedef FusedLayout<NT, UPD> LY;
     extern __shared__ double fsm[];
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double *const ring = fsm + (size_t)wy * LY::PER_WARP;   // [4][NR][RROW]
@@ -106,7 +109,11 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
         const ofs_t ro = (ofs_t)jf * nxd, q = q0 + ro, c2 = c0 + ro;
 #pragma unroll
         for (int n = 0; n < NT; n++)
-            if (a.accumulate) cp_async8(&Y[n * 32 + lane], a.th[n] + q);
+            if (!UPD && a.accumulate) cp_async8(&Y[n * 32 + lane], a.th[n] + q);
+        if (UPD) {
+            cp_async8(&Y[LY::Y_RM1 * 32 + lane], a.rho_m1 + q);
+            cp_async8(&Y[LY::Y_RR * 32 + lane], a.rho_r + q);
+        }
         cp_async8(&Y[LY::Y_V * 32 + lane], a.v + q);
         cp_async8(&Y[LY::Y_WK * 32 + lane], a.w + q + wofs);          // w3(k) = d3(k) + slab ; w3(k-1) = d3(k)
         if (has_km1) cp_async8(&Y[LY::Y_WM * 32 + lane], a.w + q);
@@ -229,8 +236,15 @@ __global__ void __launch_bounds__(32 * FWARPS, FMINB) k_sweby_xy(const Geom g, c
             for (int n = 0; n < NT; n++) {
                 if (DIAG && cell_ok && a.flux2[n]) a.flux2[n][q] = L.f[n];
                 if (L.live && cell_ok) {
-                    a.adv[n][q] = L.adv[n];
-                    if (a.accumulate) a.th[n][q] = Y[n * 32 + lane] + L.adv[n];
+                    if (UPD) {
+                        const double thv = 0.0 + L.adv[n];             // th_tendency = 0.0, then += wrk1
+                        if (a.adv[n]) a.adv[n][q] = L.adv[n];
+                        if (a.th[n]) a.th[n][q] = thv;
+                        a.Tnew[n][q] = ((Y[LY::Y_RM1 * 32 + lane] * L.Tc[n]) + (a.dtime * thv)) * Y[LY::Y_RR * 32 + lane];
+                    } else {
+                        a.adv[n][q] = L.adv[n];
+                        if (a.accumulate) a.th[n][q] = Y[n * 32 + lane] + L.adv[n];
+                    }
                     if (DIAG && VAR == VAR_ALL && a.dadv2[n]) a.dadv2[n][q] = L.wy[n];
                 }
                 L.fprev[n] = L.f[n];

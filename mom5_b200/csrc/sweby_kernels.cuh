@@ -36,6 +36,8 @@ struct SwebyArgs {
     double *flux[NT];           // optional diagnostics (data-domain layout) or nullptr
     double *dadv[NT];           // optional per-direction tendency diagnostics or nullptr
     double *flux2[NT], *dadv2[NT];   // fused x+y pass: the y sweep's diagnostics (flux/dadv are then the x sweep's)
+    double *Tnew[NT];           // fused pass with the tracer time update in its epilogue (UPD): field(taup1)
+    const double *rho_m1, *rho_r;    // UPD: rho_dzt(taum1), rho_dztr(taup1)
     const double *u, *v, *w, *rho;
     const uint8_t *nib;         // mask nibbles of this sweep's direction, data-domain layout
     const uint8_t *nib2;        // fused x+y pass: the y nibbles (nib holds the x nibbles)

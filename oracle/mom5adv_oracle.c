@@ -349,6 +349,41 @@ void orc_sweby_all_y(const orc_block *b, int ntr, double dtime, const double *co
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * compute_adv_diss (OTA:7547-7712): dissipation from advection truncation errors.  The scheme's operators are applied
+ * to the squared tracer by the caller (oracle.py: Oracle.adv_diss, same functions as the dispatcher arms); here the two
+ * element-wise parts.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_square(const orc_block *b, const double *T, double *out) /* OTA:7574-7580, data domain */
+{
+    const size_t n = (size_t)NX1(b) * NY1(b) * b->nk;
+    for (size_t q = 0; q < n; q++) out[q] = T[q] * T[q];
+}
+
+/* OTA:7680-7701.  wrk2 / wrk3 = horizontal / vertical operator on T**2 (data-domain arrays, compute domain filled);
+ * t2_tendency = wrk1 (zero outside the compute domain), diss = wrk4 (zero outside). */
+void orc_adv_diss_final(const orc_block *b, double dtime, double conversion, const double *rho_tau, const double *rho_taup1,
+                        const double *T_tau, const double *advect_tendency, const double *wrk2, const double *wrk3,
+                        double *t2_tendency, double *diss)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const size_t n = (size_t)NX1(b) * NY1(b) * nk;
+    const double dtimer = 1.0 / dtime;
+    memset(t2_tendency, 0, sizeof(double) * n);
+    memset(diss, 0, sizeof(double) * n);
+    for (int k = 1; k <= nk; k++)
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t q = D3(b, i, j, k);
+                double w1 = wrk2[q] + wrk3[q];
+                double at = advect_tendency[q];
+                double term1 = at * (((2.0 * rho_tau[q]) * T_tau[q]) + (dtime * at));
+                double term2 = -(rho_taup1[q] * w1);
+                t2_tendency[q] = w1;
+                diss[q] = (-(conversion * conversion) * dtimer) * (term1 + term2);
+            }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * advect_tracer_mdfl_sweby_test (OTA:3469-3746): the mass-weighted variant.  Three running fields on the halo-2
  * scratch: tracer_mdfl (tr), tracermass_mdfl (tms), mass_mdfl (ms); the CFL number is |massflux|*dtime/mass of
  * the upwind cell; theta's denominator is sign(1e-30,Rj)+Rj (sign BIT of Rj, as IEEE processors do).

@@ -112,6 +112,12 @@ void orc_sweby_test_x(const orc_block *b, double dtime, double sweby_limiter, co
 void orc_sweby_test_y(const orc_block *b, double dtime, double sweby_limiter, const double *T, const double *vhrho_nt,
                       const double *rho_dzt, double *tr, double *tms, double *ms, double *flux_y, double *wrk1_out);
 
+/* ---- compute_adv_diss (OTA:7547-7712): element-wise parts; the operators on T**2 are the arms above ---- */
+void orc_square(const orc_block *b, const double *T, double *out);
+void orc_adv_diss_final(const orc_block *b, double dtime, double conversion, const double *rho_tau, const double *rho_taup1,
+                        const double *T_tau, const double *advect_tendency, const double *wrk2, const double *wrk3,
+                        double *t2_tendency, double *diss);
+
 /* ---- quicker (OTA:1442-1586, 2538-2653, 2981-3031) ---- */
 void orc_quicker_init_pre(const orc_block *b);    /* fills tmask_h2/dxt_h2/dyt_h2 before their halo updates  */
 void orc_quicker_init_edges(const orc_block *b);  /* OTA:1490-1509 edge replication (after tmask update)    */

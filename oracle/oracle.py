@@ -268,6 +268,34 @@ class Oracle:
                                     _ptr(tr[ib]), _ptr(tms[ib]), _ptr(ms[ib]), _ptr(fy[ib]), _ptr(wrk1[ib]))
         return dict(wrk1=wrk1, flux_x=fx, flux_y=fy, flux_z=fz, tracer=tr, tracermass=tms, mass=ms)
 
+    def adv_diss(self, scheme: str, T_tau, tmask_limit, limit_with_upwind, advect_tendency, rho_taup1, dtime, conversion):
+        """compute_adv_diss (OTA:7547-7712) for one tracer; scheme in upwind / quicker / mdfl_sweby / dst_linear /
+        mdfl_sweby_test / dst_linear_test.  Returns dict(diss=wrk4, t2_tendency=wrk1) per block."""
+        T_tau = [_np(t) for t in T_tau]
+        sq = [b.d1() for b in self.blocks]
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_square(C.byref(b.c), _ptr(T_tau[ib]), _ptr(sq[ib]))
+        zero = [b.d1() for b in self.blocks]
+        if scheme == "upwind":
+            w2, w3 = self.horz_upwind(sq)["wrk1"], self.vert_upwind(sq)["wrk1"]
+        elif scheme == "quicker":
+            w2 = self.horz_quicker(sq, sq, tmask_limit, limit_with_upwind)["wrk1"]
+            w3 = self.vert_quicker(sq, sq, tmask_limit)["wrk1"]
+        elif scheme in ("mdfl_sweby", "dst_linear"):
+            w2, w3 = self.mdfl_sweby(sq, dtime, 1.0 if scheme == "mdfl_sweby" else 0.0)["wrk1"], zero
+        elif scheme == "dst_linear_test":
+            w2, w3 = self.sweby_test(sq, dtime, 0.0)["wrk1"], zero
+        elif scheme == "mdfl_sweby_test":      # no arm in compute_adv_diss's select (OTA:7583-7626): wrk2 stays 0
+            w2, w3 = zero, zero
+        else:
+            raise ValueError(scheme)
+        t2 = [b.d1() for b in self.blocks]; diss = [b.d1() for b in self.blocks]
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_adv_diss_final(C.byref(b.c), C.c_double(dtime), C.c_double(conversion), _ptr(self.rho[ib]),
+                                      _ptr(_np(rho_taup1[ib])), _ptr(T_tau[ib]), _ptr(_np(advect_tendency[ib])),
+                                      _ptr(w2[ib]), _ptr(w3[ib]), _ptr(t2[ib]), _ptr(diss[ib]))
+        return dict(diss=diss, t2_tendency=t2)
+
     # ---- quicker ----
     def horz_quicker(self, Tm1, Tt, tmask_limit, limit_with_upwind: bool):
         if not self._quick_ready:

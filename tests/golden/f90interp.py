@@ -227,7 +227,16 @@ _LOGICAL = [(r"\.not\.", " not "), (r"\.and\.", " and "), (r"\.or\.", " or "), (
             (r"\.gt\.", ">"), (r"\.ge\.", ">=")]
 
 
+_SQ = re.compile(r"(\((?:[^()]|\((?:[^()]|\([^()]*\))*\))*\)|[\w%]+)\s*\*\*\s*2\b")
+
+
+def fsq(x):
+    """x**2 as every Fortran compiler evaluates it: one multiplication (CPython's float ** calls libm pow)"""
+    return x * x
+
+
 def xexpr(s: str) -> str:
+    s = _SQ.sub(r"fsq(\1)", s)
     s = s.replace("%", ".")
     for pat, rep in _LOGICAL:
         s = re.sub(pat, rep, s, flags=re.I)

@@ -17,6 +17,7 @@ Routines executed from the reference text (line ranges located by their `subrout
     advect_tracer_mdfl_sweby_test .. mass-weighted variant (tracer, tracer mass and cell mass carried through the sweeps)
     horz_advect_tracer ............. dispatcher arms upwind / quicker / mdfl_sweby / dst_linear / *_test
     vert_advect_tracer ............. dispatcher arms upwind / quicker
+    compute_adv_diss ............... advective dissipation diagnostic (scheme applied to the squared tracer)
 What is NOT reference text: the halo filler standing in for FMS mpp_update_domains (single domain: cyclic
 wrap, folded north edge, walls untouched; CGRID_NE fold fix) -- that restates
 src/shared/mpp/include/mpp_domains_define.inc:4865-4885,2535-2549 and is checked separately against FMS's own
@@ -37,7 +38,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from f90interp import FArray, FList, Obj, S, nint, translate_block, translate_routine  # noqa: E402
+from f90interp import FArray, FList, Obj, S, fsq, nint, translate_block, translate_routine  # noqa: E402
 from mom5_b200.domain import XUPDATE, YUPDATE, Decomposition  # noqa: E402
 from mom5_b200.synthetic import make_case  # noqa: E402
 
@@ -122,7 +123,7 @@ def build_env(gen, b, src):
     isc, iec, jsc, jec = 1, ni, 1, nj
     isd, ied, jsd, jed = 0, ni + 1, 0, nj + 1
     dec = s.decomposition(1, 1)
-    env = dict(FArray=FArray, S=S, nint=nint, min=min, max=max, abs=abs,
+    env = dict(FArray=FArray, S=S, nint=nint, fsq=fsq, min=min, max=max, abs=abs,
                sign=lambda a, b: math.copysign(abs(a), b),   # IEEE processors: the sign BIT of b (also for b = -0.0)
                isc=isc, iec=iec, jsc=jsc, jec=jec, isd=isd, ied=ied, jsd=jsd, jed=jed, nk=nk,
                num_prog_tracers=ntr, XUPDATE=XUPDATE, YUPDATE=YUPDATE, CGRID_NE=2, FATAL=2,
@@ -158,7 +159,8 @@ def build_env(gen, b, src):
     env["T_prog"] = FList(tracers)
     d1 = lambda: FArray([(isd, ied), (jsd, jed), (1, nk)])
     h2 = lambda: FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2), (1, nk)])
-    for nm in ("flux_x", "flux_y", "flux_z", "wrk1", "advect_tendency", "neutral_temp_advect", "neutral_salt_advect"):
+    for nm in ("flux_x", "flux_y", "flux_z", "wrk1", "wrk2", "wrk3", "wrk4", "advect_tendency", "neutral_temp_advect",
+               "neutral_salt_advect"):
         env[nm] = d1()
     for nm in ("tmask_mdfl", "tracer_mdfl", "mass_mdfl", "tracermass_mdfl", "tmask_quick", "tracer_quick"):
         env[nm] = h2()
@@ -177,7 +179,10 @@ def build_env(gen, b, src):
     DIAG_IDS = ["zflux_adv", "advection_z", "xflux_adv", "advection_x", "xflux_adv_int_z", "yflux_adv", "advection_y",
                 "yflux_adv_int_z", "sweby_advect", "horz_advect", "vert_advect", "tracer_advection", "psom_advect",
                 "tracer_advection_on_nrho", "tracer_adv_diss"]
-    OFF = {"psom_advect", "tracer_advection_on_nrho", "tracer_adv_diss"}
+    OFF = {"psom_advect", "tracer_advection_on_nrho", "tracer_adv_diss"}   # run_case switches tracer_adv_diss on for the arms
+    env["__OFF__"] = OFF
+    env["index_temp_sq"] = env["index_salt_sq"] = -1
+    env["id_tracer2_advection"] = lambda n: -1
     for q, nm in enumerate(DIAG_IDS):
         env["id_" + nm] = (lambda n, q=q, nm=nm: -1 if nm in OFF else (q + 1) * 100 + n)
 
@@ -203,7 +208,7 @@ def build_env(gen, b, src):
 
     noop = lambda *a, **k: 0
     env.update(mpp_clock_begin=noop, mpp_clock_end=noop, mpp_clock_id=noop, set_ocean_domain=noop,
-               watermass_diag=noop, gyre_overturn_diagnose=noop, compute_adv_diss=noop,
+               watermass_diag=noop, gyre_overturn_diagnose=noop,
                store_ocean_obc_tracer_flux=noop, ocean_obc_zero_boundary=noop,
                mpp_update_domains=update_domains, mpp_start_update_domains=start_update,
                mpp_complete_update_domains=noop, diagnose_3d=diagnose, diagnose_2d=diagnose,
@@ -227,6 +232,9 @@ def run_case(name):
     def load_routine(kind, nm):
         first, last = find_routine(src, kind, nm)
         code, _ = translate_routine(src, first, last, array_names=arrays)
+        if nm == "compute_adv_diss":   # `logical :: use_psom=.false.` -- the translator skips declarations, initialisers included
+            head, rest = code.split("\n", 1)
+            code = head + "\n    use_psom = False\n" + rest
         exec(compile(code, f"<OTA:{first}-{last} {nm}>", "exec"), env)
         return first, last
 
@@ -235,8 +243,19 @@ def run_case(name):
                      ("function", "advect_tracer_mdfl_sweby_test"),
                      ("function", "horz_advect_tracer_upwind"), ("function", "vert_advect_tracer_upwind"),
                      ("function", "horz_advect_tracer_quicker"), ("function", "vert_advect_tracer_quicker"),
+                     ("subroutine", "compute_adv_diss"),
                      ("subroutine", "horz_advect_tracer"), ("subroutine", "vert_advect_tracer")):
         cites[nm] = load_routine(kind, nm)
+
+    # compute_adv_diss re-runs the advection functions on the squared tracer, which overwrites the module-level flux
+    # arrays: keep flux_z as it was when vert_advect_tracer sent its diagnostics
+    real_adv_diss, snap = env["compute_adv_diss"], {}
+
+    def adv_diss_hook(*a, **k):
+        snap["flux_z"] = env["flux_z"].a.copy()
+        return real_adv_diss(*a, **k)
+
+    env["compute_adv_diss"] = adv_diss_hook
 
     out = {}
     # ---- mdfl_init: mask fill + halo update (tmask_mdfl = 0.0 ... mpp_update_domains) ----
@@ -270,8 +289,9 @@ def run_case(name):
         out[f"sweby_all.diag.{k}"] = v
     print(f"  sweby_all: {time.time() - t0:.1f}s, {len(diags)} diagnostics")
 
-    # ---- per-tracer dispatcher arms ----
+    # ---- per-tracer dispatcher arms (with the advective-dissipation diagnostic of vert_advect_tracer's tail) ----
     env["advect_sweby_all"] = False
+    env["__OFF__"].discard("tracer_adv_diss")
     f0, l0 = find_routine(src, "subroutine", "quicker_init")
     a = find_line(src, r"^\s*quick_x\s*=\s*0\.0", f0)
     z = find_line(src, r"curv_zn\(k,3\)", a) + 1  # through the enddo of the k loop
@@ -290,6 +310,7 @@ def run_case(name):
         env["limit_with_upwind"] = lim
         n = min(2, ntr) if tag in ("quicker_lim", "dst_linear_test") else 1
         tr = T_prog(n)
+        tr.conversion = 3992.1 if n == 1 else 1.0     # only compute_adv_diss output is kept from the diagnostics of the arms
         tr.horz_advect_scheme = tr.vert_advect_scheme = env[scheme]
         env["horz_advect_tracer"](env["Time"], env["Adv_vel"], env["Thickness"], env["Dens"], T_prog, tr, n, s.dtime)
         out[f"{tag}.horz.wrk1"] = tr.wrk1.a.copy()
@@ -302,8 +323,12 @@ def run_case(name):
         env["vert_advect_tracer"](env["Time"], env["Adv_vel"], env["Dens"], env["Thickness"], T_prog, tr, n, s.dtime)
         out[f"{tag}.vert.wrk1"] = tr.wrk1.a.copy()
         out[f"{tag}.vert.th_tendency"] = tr.th_tendency.a.copy()
-        out[f"{tag}.flux_z"] = env["flux_z"].a.copy()
+        out[f"{tag}.flux_z"] = snap["flux_z"]
+        out[f"{tag}.adv_diss"] = diags[f"tracer_adv_diss.{n}"].copy()          # wrk4 of compute_adv_diss
+        out[f"{tag}.adv_diss.t2_tendency"] = env["wrk1"].a.copy()             # advection operator on the squared tracer
+        out[f"{tag}.advect_tendency"] = env["advect_tendency"].a.copy()
         out[f"{tag}.tracer"] = np.array(n)
+        out[f"{tag}.conversion"] = np.array(tr.conversion)
         print(f"  {tag}: {time.time() - t0:.1f}s")
 
     # ---- continuity: diverge_t + wrho_bt recurrence (ocean_advection_velocity.F90 C-grid block; BDX_ET / BDY_NT) ----

@@ -206,8 +206,9 @@ def test_tiny_and_underflowing_tracers_take_the_exact_division_path(case):
             assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {nm}[{n}]")
 
 
-@pytest.mark.parametrize("case", ["mini_tripolar", "mini_walls", "mini_torus"])
-def test_advection_only_time_stepping(case):
+@pytest.mark.parametrize("fused_update", [False, True])
+@pytest.mark.parametrize("case", ["mini_tripolar", "mini_walls", "mini_torus", "global_1deg"])
+def test_advection_only_time_stepping(case, fused_update, sweep_mode):
     """update_advection_only (ocean_tracer.F90:2618-2649) for a few steps: tendency from the advection path, then
     field(taup1) = (rho_dzt*T + dtime*th)*rho_dztr (ocean_tracer.F90:2341-2350) and the halo-1 update of the new field
     (ocean_model.F90:1903-1911).  Sweby (all tracers) and upwind (reads the halo of T) must track the oracle bit for bit."""
@@ -215,7 +216,9 @@ def test_advection_only_time_stepping(case):
     from mom5_b200.api import ADVECT_UPWIND, TracerAdvect
     from mom5_b200.synthetic import make_case
     from oracle.oracle import Oracle, _ptr
-    g = make_case(case)
+    if fused_update and sweep_mode == "unfused":
+        pytest.skip("the fused time update lives in the fused x/y pass")
+    g = make_case(case, **(dict(ni=130, nj=70, nk=20, ntr=4) if case == "global_1deg" else {}))
     b = g.block()
     dec = g.s.decomposition(1, 1)
     o = Oracle(dec, [b])
@@ -248,6 +251,20 @@ def test_advection_only_time_stepping(case):
     for step in range(3):
         th = [torch.zeros_like(t) for t in T]
         wrk = [torch.empty_like(t) for t in T]
+        if step < 2 and fused_update:
+            # one call: z sweep + x/y pass with the time update in its epilogue + halo-1 update; th / wrk1 only on step 0
+            Tn = [t.clone() for t in T]
+            adv.advect_sweby_all_and_update(T, Tn, drho, drhor, u, v, w, drho, dt, th_tendency=th if step == 0 else None,
+                                            adv_tendency=wrk if step == 0 else None)
+            if step == 0:
+                th_chk = [torch.zeros_like(t) for t in T]
+                wrk_chk = [torch.empty_like(t) for t in T]
+                adv.advect_tracer_sweby_all(T, th_chk, wrk_chk, u, v, w, drho, dt)
+                for n in range(ntr):
+                    assert_bit_equal(th[n][:, 1:-1, 1:-1], th_chk[n][:, 1:-1, 1:-1], f"th[{n}] from the fused epilogue")
+                    assert_bit_equal(wrk[n], wrk_chk[n], f"wrk1[{n}] from the fused epilogue")
+            T = Tn
+            continue
         if step < 2:
             adv.advect_tracer_sweby_all(T, th, wrk, u, v, w, drho, dt)
         else:
@@ -260,6 +277,49 @@ def test_advection_only_time_stepping(case):
     torch.cuda.synchronize()
     for n in range(ntr):
         assert_bit_equal(T[n], Tref[n], f"{case} T[{n}] after 3 steps")
+    adv.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test"])
+def test_adv_diss_vs_reference_golden(name, tag, sweep_mode):
+    """compute_adv_diss (OTA:7547-7712) on device: operators on the squared tracer + the dissipation formula"""
+    from mom5_b200.api import SCHEME_IDS, TracerAdvect
+    b, gold, _ = load_golden(name)
+    n = int(gold[f"{tag}.tracer"]) - 1
+    scheme = SCHEME_IDS[tag.replace("_lim", "")]
+    adv = TracerAdvect(b, ntracers_max=1, limit_with_upwind=(tag == "quicker_lim"))
+    rho = _dev(b.rho_dzt)
+    diss = torch.full_like(rho, -777.0)
+    t2 = torch.full_like(rho, -777.0)
+    adv.adv_diss(scheme, scheme, _dev(b.T_tau[n]), torch.from_numpy(gold[f"{tag}.advect_tendency"]).cuda(), _dev(b.uhrho_et),
+                 _dev(b.vhrho_nt), _dev(b.wrho_bt), rho, _dev(b.rho_dzt * 1.01), b.spec.dtime, diss,
+                 conversion=float(gold[f"{tag}.conversion"]), tmask_limit=_dev(b.tmask_limit[n]), t2_tendency=t2)
+    torch.cuda.synchronize()
+    assert_bit_equal(t2, gold[f"{tag}.adv_diss.t2_tendency"], "advection of the squared tracer")
+    assert_bit_equal(diss, gold[f"{tag}.adv_diss"], "adv_diss")
+    adv.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_z_integrated_fluxes_vs_reference_golden(name, sweep_mode):
+    """*_xflux_adv_int_z / *_yflux_adv_int_z (OTA:4317-4326, 4449-4458) from the device fluxes of sweby_all"""
+    from mom5_b200.api import TracerAdvect
+    b, gold, _ = load_golden(name)
+    ntr = len(b.T)
+    adv = TracerAdvect(b, ntracers_max=ntr)
+    T = [_dev(t) for t in b.T]
+    th = [_dev(t).clone() for t in b.th_tendency]
+    out = [torch.empty_like(t) for t in T]
+    fx, fy = [torch.zeros_like(t) for t in T], [torch.zeros_like(t) for t in T]
+    adv.advect_tracer_sweby_all(T, th, out, _dev(b.uhrho_et), _dev(b.vhrho_nt), _dev(b.wrho_bt), _dev(b.rho_dzt), b.spec.dtime,
+                                flux_x=fx, flux_y=fy)
+    for n in range(ntr):
+        for f, nm in ((fx[n], "xflux_adv_int_z"), (fy[n], "yflux_adv_int_z")):
+            o2 = torch.full_like(f[0], -777.0)
+            adv.flux_int_z(f, o2)
+            torch.cuda.synchronize()
+            assert_bit_equal(o2, gold[f"sweby_all.diag.{nm}.{n + 1}"], f"{nm}[{n + 1}]")
     adv.close()
 
 

@@ -95,6 +95,20 @@ def test_mdfl_sweby_test_variant(name, tag, sl):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test"])
+def test_compute_adv_diss(name, tag):
+    """compute_adv_diss (OTA:7547-7712): the scheme applied to the squared tracer, then the dissipation formula"""
+    b, gold, _ = load_golden(name)
+    _, o = _oracle(b)
+    n = int(gold[f"{tag}.tracer"])
+    out = o.adv_diss(tag.replace("_lim", ""), [b.T_tau[n - 1].numpy()], [b.tmask_limit[n - 1].numpy()], tag == "quicker_lim",
+                     [gold[f"{tag}.advect_tendency"]], [b.rho_dzt.numpy() * 1.01], b.spec.dtime, float(gold[f"{tag}.conversion"]))
+    assert_bit_equal(out["t2_tendency"][0], gold[f"{tag}.adv_diss.t2_tendency"], "advection of the squared tracer")
+    assert_bit_equal(out["diss"][0], gold[f"{tag}.adv_diss"], "adv_diss")
+    assert np.abs(gold[f"{tag}.adv_diss"]).max() > 0
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_quicker_init(name):
     b, gold, _ = load_golden(name)
     _, o = _oracle(b)

@@ -349,6 +349,222 @@ void orc_sweby_all_y(const orc_block *b, int ntr, double dtime, const double *co
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * advect_tracer_mdppm (OTA:5990-6494) with ppm_limit_cw84 / _ifc / _sh (OTA:6510-6657): multi-dimensional
+ * piecewise-parabolic scheme; tracer_mdppm and tmask_mdppm live on a halo-4 scratch (h4).
+ * ---------------------------------------------------------------------------------------------- */
+#define NX4(b) ((b)->ni + 8)
+#define NY4(b) ((b)->nj + 8)
+#define Q2(b, i, j) ((size_t)((i) + 3) + (size_t)NX4(b) * (size_t)((j) + 3))                 /* 2-D h4 work arrays */
+#define Q3(b, i, j, k) (Q2(b, i, j) + (size_t)NX4(b) * NY4(b) * (size_t)((k)-1))             /* i, j = -3 .. n+4 */
+static const double R12 = 1. / 12., TWOTHIRDS = 2. / 3., FOURTHIRDS = 4. / 3.;
+
+static inline double max3(double a, double b, double c) { return orc_max(orc_max(a, b), c); }
+static inline double min3(double a, double b, double c) { return orc_min(orc_min(a, b), c); }
+static inline double max4(double a, double b, double c, double d) { return orc_max(max3(a, b, c), d); }
+static inline double min4(double a, double b, double c, double d) { return orc_min(min3(a, b, c), d); }
+
+/* slope estimate + monotonic constraint (OTA:6060-6098, 6214-6245, 6349-6380); S = Sim2,Sim1,Si,Sip1,Sip2, m likewise */
+static inline double ppm_slope(const double *S, const double *m)
+{
+    double da2 = 0.5 * (S[3] - S[1]);
+    double da3m = R12 * ((((2. * S[0]) - (12. * S[1])) + (6. * S[2])) + (4. * S[3]));
+    double da3p = R12 * ((((-(4. * S[1])) - (6. * S[2])) + (12. * S[3])) - (2. * S[4]));
+    double da = (((m[0] * (1. - (0.5 * m[4]))) * da3m) + ((m[4] * (1. - (0.5 * m[0]))) * da3p)) + (((1. - m[0]) * (1. - m[4])) * da2);
+    double dMx = max3(S[3], S[1], S[2]) - S[2];
+    double dMn = S[2] - min3(S[3], S[1], S[2]);
+    return (((copysign(1., da) * orc_min(fabs(da), 2. * orc_min(dMx, dMn))) * m[1]) * m[3]) * m[2];
+}
+
+typedef struct { double d1m, d1p, d1mm, d1pp; } ppm_d1;
+static inline ppm_d1 ppm_diffs(const double *S, const double *m)
+{
+    ppm_d1 d;
+    d.d1m = (S[2] - S[1]) * m[1];
+    d.d1p = (S[3] - S[2]) * m[3];
+    d.d1mm = ((S[1] - S[0]) * m[1]) * m[0];
+    d.d1pp = ((S[4] - S[3]) * m[3]) * m[4];
+    return d;
+}
+
+/* edge values (Lin 1994 eq. B2) then one of the three limiters, all point-wise */
+static inline void ppm_edges(int limiter, double Si, ppm_d1 d, double da_m, double da_0, double da_p, double *aLo, double *aRo)
+{
+    double Sim1 = Si - d.d1m, Sip1 = Si + d.d1p;
+    double aL = (0.5 * (Sim1 + Si)) + (ONESIXTH * (da_m - da_0));
+    double aR = (0.5 * (Si + Sip1)) + (ONESIXTH * (da_0 - da_p));
+    if (limiter == 1) { /* ppm_limit_cw84, OTA:6520-6536 */
+        if ((aR - Si) * (Si - aL) <= 0.) { aL = Si; aR = Si; }
+        double da2 = aR - aL, da4 = 0.5 * (aR + aL);
+        double da3m = (6. * da2) * (Si - da4), da3p = da2 * da2;
+        if (da3m > da3p) aL = (3. * Si) - (2. * aR);
+        if (da3m < -da3p) aR = (3. * Si) - (2. * aL);
+    } else if (limiter == 2) { /* ppm_limit_ifc, OTA:6565-6575 */
+        double ada = fabs(da_0), sda = copysign(1., da_0);
+        aL = Si - (sda * orc_min(ada, fabs(aL - Si)));
+        aR = Si + (sda * orc_min(ada, fabs(aR - Si)));
+    } else { /* ppm_limit_sh, OTA:6614-6655 */
+        double z = d.d1m - d.d1mm, w = d.d1p - d.d1m;
+        double x = (4. * w) - z, y = (4. * z) - w;
+        double dM4m = orc_max(0., min4(x, y, z, w)) + orc_min(0., max4(x, y, z, w));
+        z = d.d1pp - d.d1p;
+        x = (4. * w) - z;
+        y = (4. * z) - w;
+        double dM4p = orc_max(0., min4(x, y, z, w)) + orc_min(0., max4(x, y, z, w));
+        double qAV = 0.5 * (Si + Sip1);
+        x = d.d1p;
+        y = 3. * d.d1m;
+        double qMP = (Si + orc_max(0., orc_min(x, y))) + orc_min(0., orc_max(x, y));
+        double qUL = Si + y;
+        double qLC = (Si + (0.5 * d.d1m)) + (FOURTHIRDS * dM4m);
+        double qMD = qAV - (0.5 * dM4p);
+        double qMin = orc_max(min3(qMD, Si, Sip1), min3(Si, qUL, qLC));
+        double qMax = orc_min(max3(qMD, Si, Sip1), max3(Si, qUL, qLC));
+        if ((aR - Si) * (aR - qMP) > 1.e-10) aR = orc_min(orc_max(aR, qMin), qMax);
+        qAV = 0.5 * (Si + Sim1);
+        x = -d.d1m;
+        y = -3. * d.d1p;
+        qMP = (Si + orc_max(0., orc_min(x, y))) + orc_min(0., orc_max(x, y));
+        qUL = Si + y;
+        qLC = (Si - (0.5 * d.d1p)) + (FOURTHIRDS * dM4p);
+        qMD = qAV - (0.5 * dM4m);
+        qMin = orc_max(min3(qMD, Si, Sim1), min3(Si, qUL, qLC));
+        qMax = orc_min(max3(qMD, Si, Sim1), max3(Si, qUL, qLC));
+        if ((aL - Si) * (aL - qMP) > 1.e-10) aL = orc_min(orc_max(aL, qMin), qMax);
+    }
+    *aLo = aL;
+    *aRo = aR;
+}
+
+/* OTA:6036-6201: vertical fluxes and update.  tr (h4) := 0, compute domain := updated tracer; flux_z on the compute domain. */
+void orc_mdppm_z(const orc_block *b, double dtime, int limiter, const double *T, const double *w, const double *rho,
+                 const double *m4, double *tr, double *flux_z)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    memset(tr, 0, sizeof(double) * (size_t)NX4(b) * NY4(b) * nk);
+    double *dak = (double *)calloc((size_t)nk + 2, sizeof(double)), *aL = (double *)calloc((size_t)nk + 2, sizeof(double));
+    double *aR = (double *)calloc((size_t)nk + 2, sizeof(double));
+    for (int j = 1; j <= nj; j++)
+        for (int i = 1; i <= ni; i++) {
+            double S[5], m[5];
+#define ZCELL(k)                                                                                              \
+    do {                                                                                                      \
+        int km2 = imax((k)-2, 1), km1 = imax((k)-1, 1), kp1 = imin((k) + 1, nk), kp2 = imin((k) + 2, nk);     \
+        S[0] = T[D3(b, i, j, km2)]; S[1] = T[D3(b, i, j, km1)]; S[2] = T[D3(b, i, j, (k))];                   \
+        S[3] = T[D3(b, i, j, kp1)]; S[4] = T[D3(b, i, j, kp2)];                                               \
+        m[0] = m4[Q3(b, i, j, km2)] * (double)(km1 - km2); m[1] = m4[Q3(b, i, j, km1)] * (double)((k)-km1);   \
+        m[2] = m4[Q3(b, i, j, (k))];                                                                          \
+        m[3] = m4[Q3(b, i, j, kp1)] * (double)(kp1 - (k)); m[4] = m4[Q3(b, i, j, kp2)] * (double)(kp2 - kp1); \
+    } while (0)
+            for (int k = 1; k <= nk; k++) { ZCELL(k); dak[k] = ppm_slope(S, m); }
+            for (int k = 1; k <= nk; k++) {
+                int km1 = imax(k - 1, 1), kp1 = imin(k + 1, nk);
+                ZCELL(k);
+                ppm_edges(limiter, S[2], ppm_diffs(S, m), dak[km1], dak[k], dak[kp1], &aL[k], &aR[k]);
+                double a6 = (6. * S[2]) - (3. * (aR[k] + aL[k]));
+                double dat = b->dat[D2(b, i, j)];
+                double massflux = ((dat * w[W3(b, i, j, k)]) * m[2]) * m[3];
+                if (massflux <= 0.0) {
+                    double cfl = fabs((w[W3(b, i, j, k)] * dtime) / rho[D3(b, i, j, k)]);
+                    flux_z[D3(b, i, j, k)] = massflux * (aR[k] + ((0.5 * cfl) * ((aL[k] - aR[k]) + ((1. - (TWOTHIRDS * cfl)) * a6))));
+                }
+                massflux = ((dat * w[W3(b, i, j, km1)]) * m[2]) * m[1];
+                if (massflux > 0.0) {
+                    double cfl = fabs((w[W3(b, i, j, km1)] * dtime) / rho[D3(b, i, j, km1)]);
+                    flux_z[D3(b, i, j, km1)] = massflux * (aL[k] + ((0.5 * cfl) * ((aR[k] - aL[k]) + ((1. - (TWOTHIRDS * cfl)) * a6))));
+                }
+            }
+#undef ZCELL
+            for (int k = 1; k <= nk; k++) { /* OTA:6180-6190 */
+                int km1 = imax(k - 1, 1);
+                double mskm1 = (double)(k - km1), Tk = T[D3(b, i, j, k)];
+                tr[Q3(b, i, j, k)] = Tk + ((dtime / rho[D3(b, i, j, k)]) *
+                                           ((b->datr[D2(b, i, j)] * (flux_z[D3(b, i, j, k)] - (mskm1 * flux_z[D3(b, i, j, km1)]))) +
+                                            (Tk * ((mskm1 * w[W3(b, i, j, km1)]) - w[W3(b, i, j, k)]))));
+            }
+        }
+    free(dak); free(aL); free(aR);
+}
+
+/* one horizontal direction: dir 0 = x (OTA:6205-6328), 1 = y (OTA:6344-6455); fluxes only */
+static void mdppm_hflux(const orc_block *b, double dtime, int limiter, int dir, const double *vel, const double *rho,
+                        const double *m4, const double *tr, double *flux)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    const int di = dir == 0, dj = dir == 1;
+    const size_t n2 = (size_t)NX4(b) * NY4(b);
+    double *da = (double *)calloc(n2, sizeof(double)), *aL = (double *)calloc(n2, sizeof(double));
+    double *aR = (double *)calloc(n2, sizeof(double)), *a6 = (double *)calloc(n2, sizeof(double));
+    ppm_d1 *dd = (ppm_d1 *)calloc(n2, sizeof(ppm_d1));
+    const double *met_f = dir == 0 ? b->dyte : b->dxtn, *met_c = dir == 0 ? b->dxte : b->dytn;
+    for (int k = 1; k <= nk; k++) {
+        for (int j = 1 - 2 * dj; j <= nj + 2 * dj; j++)
+            for (int i = 1 - 2 * di; i <= ni + 2 * di; i++) {
+                double S[5], m[5];
+                for (int q = 0; q < 5; q++) {
+                    S[q] = tr[Q3(b, i + (q - 2) * di, j + (q - 2) * dj, k)];
+                    m[q] = m4[Q3(b, i + (q - 2) * di, j + (q - 2) * dj, k)];
+                }
+                da[Q2(b, i, j)] = ppm_slope(S, m);
+                dd[Q2(b, i, j)] = ppm_diffs(S, m);
+            }
+        for (int j = 1 - dj; j <= nj + dj; j++)
+            for (int i = 1 - di; i <= ni + di; i++) {
+                double Si = tr[Q3(b, i, j, k)];
+                ppm_edges(limiter, Si, dd[Q2(b, i, j)], da[Q2(b, i - di, j - dj)], da[Q2(b, i, j)], da[Q2(b, i + di, j + dj)],
+                          &aL[Q2(b, i, j)], &aR[Q2(b, i, j)]);
+                a6[Q2(b, i, j)] = (6. * Si) - (3. * (aR[Q2(b, i, j)] + aL[Q2(b, i, j)]));
+            }
+        for (int j = 1 - dj; j <= nj; j++)
+            for (int i = 1 - di; i <= ni; i++) {
+                double vv = vel[D3(b, i, j, k)];
+                double massflux = met_f[D2(b, i, j)] * vv;
+                double cfl = ((vv * dtime) * 2.0) / ((rho[D3(b, i, j, k)] + rho[D3(b, i + di, j + dj, k)]) * met_c[D2(b, i, j)]);
+                double mm = (massflux * m4[Q3(b, i, j, k)]) * m4[Q3(b, i + di, j + dj, k)];
+                size_t c = Q2(b, i, j), e = Q2(b, i + di, j + dj);
+                if (massflux >= 0.0)
+                    flux[D3(b, i, j, k)] = mm * (aR[c] + ((0.5 * cfl) * ((aL[c] - aR[c]) + ((1. - (TWOTHIRDS * cfl)) * a6[c]))));
+                else
+                    flux[D3(b, i, j, k)] = mm * (aL[e] - ((0.5 * cfl) * ((aR[e] - aL[e]) + ((1. + (TWOTHIRDS * cfl)) * a6[e]))));
+            }
+    }
+    free(da); free(aL); free(aR); free(a6); free(dd);
+}
+
+void orc_mdppm_x(const orc_block *b, double dtime, int limiter, const double *T, const double *u, const double *rho,
+                 const double *m4, double *tr, double *flux_x)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    mdppm_hflux(b, dtime, limiter, 0, u, rho, m4, tr, flux_x);
+    for (int k = 1; k <= nk; k++) /* OTA:6317-6327 */
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++)
+                tr[Q3(b, i, j, k)] = tr[Q3(b, i, j, k)] +
+                                     ((((dtime * m4[Q3(b, i, j, k)]) * b->datr[D2(b, i, j)]) / rho[D3(b, i, j, k)]) *
+                                      ((flux_x[D3(b, i - 1, j, k)] - flux_x[D3(b, i, j, k)]) +
+                                       (T[D3(b, i, j, k)] * ((b->dyte[D2(b, i, j)] * u[D3(b, i, j, k)]) - (b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)])))));
+}
+
+/* y sweep + overall tendency; wrk1_out = Tracer%wrk1 (the dispatcher's negation, OTA:1966-1968, applied) */
+void orc_mdppm_y(const orc_block *b, double dtime, int limiter, const double *T, const double *u, const double *v, const double *w,
+                 const double *rho, const double *m4, double *tr, double *flux_y, double *wrk1_out)
+{
+    const int ni = b->ni, nj = b->nj, nk = b->nk;
+    mdppm_hflux(b, dtime, limiter, 1, v, rho, m4, tr, flux_y);
+    for (int k = 1; k <= nk; k++)
+        for (int j = 1; j <= nj; j++)
+            for (int i = 1; i <= ni; i++) {
+                size_t q = D3(b, i, j, k), c = D2(b, i, j);
+                double t = tr[Q3(b, i, j, k)] + ((((dtime * b->tmask[q]) * b->datr[c]) / rho[q]) * (flux_y[D3(b, i, j - 1, k)] - flux_y[q]));
+                double wkm1 = (k > 1) ? w[W3(b, i, j, k - 1)] : 0.0;
+                t = t + (((dtime * T[q]) / rho[q]) *
+                         ((w[W3(b, i, j, k)] - wkm1) + (b->datr[c] * ((b->dyte[D2(b, i - 1, j)] * u[D3(b, i - 1, j, k)]) - (b->dyte[c] * u[q])))));
+                tr[Q3(b, i, j, k)] = t;
+                double f = (((-rho[q]) * (t - T[q])) / dtime) * m4[Q3(b, i, j, k)];
+                wrk1_out[q] = -f;
+            }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * compute_adv_diss (OTA:7547-7712): dissipation from advection truncation errors.  The scheme's operators are applied
  * to the squared tracer by the caller (oracle.py: Oracle.adv_diss, same functions as the dispatcher arms); here the two
  * element-wise parts.

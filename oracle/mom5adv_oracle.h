@@ -112,6 +112,16 @@ void orc_sweby_test_x(const orc_block *b, double dtime, double sweby_limiter, co
 void orc_sweby_test_y(const orc_block *b, double dtime, double sweby_limiter, const double *T, const double *vhrho_nt,
                       const double *rho_dzt, double *tr, double *tms, double *ms, double *flux_y, double *wrk1_out);
 
+/* ---- advect_tracer_mdppm (OTA:5990-6494) + ppm_limit_cw84/_ifc/_sh (OTA:6510-6657), one tracer.  m4 = tmask_mdppm and
+ *      tr = tracer_mdppm on the halo-4 scratch, dims (ni+8, nj+8, nk); XUPDATE of tr (halo 4) between z and x, YUPDATE
+ *      between x and y.  limiter = Tracer%ppm_hlimiter (1 cw84, 2 ifc, 3 sh; the reference uses it in all directions). ---- */
+void orc_mdppm_z(const orc_block *b, double dtime, int limiter, const double *T, const double *wrho_bt, const double *rho_dzt,
+                 const double *m4, double *tr, double *flux_z);
+void orc_mdppm_x(const orc_block *b, double dtime, int limiter, const double *T, const double *uhrho_et, const double *rho_dzt,
+                 const double *m4, double *tr, double *flux_x);
+void orc_mdppm_y(const orc_block *b, double dtime, int limiter, const double *T, const double *uhrho_et, const double *vhrho_nt,
+                 const double *wrho_bt, const double *rho_dzt, const double *m4, double *tr, double *flux_y, double *wrk1_out);
+
 /* ---- compute_adv_diss (OTA:7547-7712): element-wise parts; the operators on T**2 are the arms above ---- */
 void orc_square(const orc_block *b, const double *T, double *out);
 void orc_adv_diss_final(const orc_block *b, double dtime, double conversion, const double *rho_tau, const double *rho_taup1,

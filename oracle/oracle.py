@@ -109,6 +109,9 @@ class Block:
     def h2(self):
         return np.zeros((self.nk, self.nj + 4, self.ni + 4))
 
+    def h4(self):
+        return np.zeros((self.nk, self.nj + 8, self.ni + 8))
+
     def d1(self):
         return np.zeros((self.nk, self.nj + 2, self.ni + 2))
 
@@ -268,6 +271,37 @@ class Oracle:
                                     _ptr(tr[ib]), _ptr(tms[ib]), _ptr(ms[ib]), _ptr(fy[ib]), _ptr(wrk1[ib]))
         return dict(wrk1=wrk1, flux_x=fx, flux_y=fy, flux_z=fz, tracer=tr, tracermass=tms, mass=ms)
 
+    def mdppm_init(self):
+        """mdppm_init (OTA:1714-1726): tmask_mdppm with a full halo-4 update"""
+        self.m4 = []
+        for b in self.blocks:
+            m = b.h4()
+            m[:, 4:-4, 4:-4] = b.tmask[:, 1:-1, 1:-1]
+            self.m4.append(m)
+        self.update(self.m4, 4, XUPDATE | YUPDATE)
+
+    def mdppm(self, T: List[np.ndarray], dtime: float, limiter: int = 1):
+        """advect_tracer_mdppm (OTA:5990-6494) behind the dispatcher arm OTA:1966-1968"""
+        if not hasattr(self, "m4"):
+            self.mdppm_init()
+        T = [_np(t) for t in T]
+        tr = [b.h4() for b in self.blocks]
+        fx = [b.d1() for b in self.blocks]; fy = [b.d1() for b in self.blocks]; fz = [b.d1() for b in self.blocks]
+        wrk1 = [b.d1() for b in self.blocks]
+        dt, lim = C.c_double(dtime), C.c_int(limiter)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_mdppm_z(C.byref(b.c), dt, lim, _ptr(T[ib]), _ptr(self.w[ib]), _ptr(self.rho[ib]), _ptr(self.m4[ib]),
+                               _ptr(tr[ib]), _ptr(fz[ib]))
+        self.update(tr, 4, XUPDATE)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_mdppm_x(C.byref(b.c), dt, lim, _ptr(T[ib]), _ptr(self.u[ib]), _ptr(self.rho[ib]), _ptr(self.m4[ib]),
+                               _ptr(tr[ib]), _ptr(fx[ib]))
+        self.update(tr, 4, YUPDATE)
+        for ib, b in enumerate(self.blocks):
+            self.L.orc_mdppm_y(C.byref(b.c), dt, lim, _ptr(T[ib]), _ptr(self.u[ib]), _ptr(self.v[ib]), _ptr(self.w[ib]),
+                               _ptr(self.rho[ib]), _ptr(self.m4[ib]), _ptr(tr[ib]), _ptr(fy[ib]), _ptr(wrk1[ib]))
+        return dict(wrk1=wrk1, flux_x=fx, flux_y=fy, flux_z=fz, tracer=tr)
+
     def adv_diss(self, scheme: str, T_tau, tmask_limit, limit_with_upwind, advect_tendency, rho_taup1, dtime, conversion):
         """compute_adv_diss (OTA:7547-7712) for one tracer; scheme in upwind / quicker / mdfl_sweby / dst_linear /
         mdfl_sweby_test / dst_linear_test.  Returns dict(diss=wrk4, t2_tendency=wrk1) per block."""
@@ -285,6 +319,8 @@ class Oracle:
             w2, w3 = self.mdfl_sweby(sq, dtime, 1.0 if scheme == "mdfl_sweby" else 0.0)["wrk1"], zero
         elif scheme == "dst_linear_test":
             w2, w3 = self.sweby_test(sq, dtime, 0.0)["wrk1"], zero
+        elif scheme.startswith("mdppm"):
+            w2, w3 = self.mdppm(sq, dtime, {"mdppm_cw84": 1, "mdppm_ifc": 2, "mdppm_sh": 3}[scheme])["wrk1"], zero
         elif scheme == "mdfl_sweby_test":      # no arm in compute_adv_diss's select (OTA:7583-7626): wrk2 stays 0
             w2, w3 = zero, zero
         else:

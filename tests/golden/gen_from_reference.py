@@ -14,6 +14,7 @@ Routines executed from the reference text (line ranges located by their `subrout
     mdfl_init (mask part) .......... tmask_mdfl
     quicker_init (weights part) .... quick_*, curv_*, dxt_quick, tmask_quick
     advect_tracer_sweby_all ........ th_tendency, T_prog%wrk1, all registered diagnostics
+    advect_tracer_mdppm + ppm_limit_cw84 / _ifc / _sh ... piecewise-parabolic scheme, halo 4, three limiters
     advect_tracer_mdfl_sweby_test .. mass-weighted variant (tracer, tracer mass and cell mass carried through the sweeps)
     horz_advect_tracer ............. dispatcher arms upwind / quicker / mdfl_sweby / dst_linear / *_test
     vert_advect_tracer ............. dispatcher arms upwind / quicker
@@ -123,7 +124,8 @@ def build_env(gen, b, src):
     isc, iec, jsc, jec = 1, ni, 1, nj
     isd, ied, jsd, jed = 0, ni + 1, 0, nj + 1
     dec = s.decomposition(1, 1)
-    env = dict(FArray=FArray, S=S, nint=nint, fsq=fsq, min=min, max=max, abs=abs,
+    env = dict(FArray=FArray, S=S, nint=nint, fsq=fsq, min=min, max=max, abs=abs, real=float,
+               oneSixth=1. / 6., r12=1. / 12., twoThirds=2. / 3., fourThirds=4. / 3.,   # `real, parameter ::` locals of the PPM routines
                sign=lambda a, b: math.copysign(abs(a), b),   # IEEE processors: the sign BIT of b (also for b = -0.0)
                isc=isc, iec=iec, jsc=jsc, jec=jec, isd=isd, ied=ied, jsd=jsd, jed=jed, nk=nk,
                num_prog_tracers=ntr, XUPDATE=XUPDATE, YUPDATE=YUPDATE, CGRID_NE=2, FATAL=2,
@@ -155,7 +157,7 @@ def build_env(gen, b, src):
                            wrk1=FArray([(isd, ied), (jsd, jed), (1, nk)], fill=-777.0),
                            tmask_limit=to_farray(b.tmask_limit[n], [isd, jsd, 1]),
                            conversion=1.0, complete=(n == ntr - 1), name=f"tr{n + 1}",
-                           horz_advect_scheme=0, vert_advect_scheme=0))
+                           horz_advect_scheme=0, vert_advect_scheme=0, ppm_hlimiter=1, ppm_vlimiter=1))
     env["T_prog"] = FList(tracers)
     d1 = lambda: FArray([(isd, ied), (jsd, jed), (1, nk)])
     h2 = lambda: FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2), (1, nk)])
@@ -164,6 +166,9 @@ def build_env(gen, b, src):
         env[nm] = d1()
     for nm in ("tmask_mdfl", "tracer_mdfl", "mass_mdfl", "tracermass_mdfl", "tmask_quick", "tracer_quick"):
         env[nm] = h2()
+    for nm in ("tmask_mdppm", "tracer_mdppm"):     # halo 4 (OTA:1706-1710)
+        env[nm] = FArray([(isc - 4, iec + 4), (jsc - 4, jec + 4), (1, nk)])
+    env["Dom_mdppm"] = Obj(domain2d="halo")
     env["tracer_mdfl_all"] = FList([Obj(field=h2()) for _ in range(ntr)])
     env["dxt_quick"] = FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2)])
     env["dyt_quick"] = FArray([(isc - 2, iec + 2), (jsc - 2, jec + 2)])
@@ -229,9 +234,14 @@ def run_case(name):
     s = gen.s
     arrays = [k for k, v in env.items() if isinstance(v, FArray)]
 
+    # Sequence association: advect_tracer_mdppm passes the level-k slab of a halo-4 array to the limiter kernels by its first
+    # element, `tracer_mdppm(isc-4,jsc-4,k)`, received as dimension(isc-4:iec+4,jsc-4:jec+4).  The translator has no
+    # storage association, so those actual arguments are rewritten as the equivalent array sections.
+    src_sa = [l.replace("tracer_mdppm(isc-4,jsc-4,k)", "tracer_mdppm(:,:,k)").replace("dak(isc-4,jsc-4,k)", "dak(:,:,k)") for l in src]
+
     def load_routine(kind, nm):
         first, last = find_routine(src, kind, nm)
-        code, _ = translate_routine(src, first, last, array_names=arrays)
+        code, _ = translate_routine(src_sa if nm == "advect_tracer_mdppm" else src, first, last, array_names=arrays)
         if nm == "compute_adv_diss":   # `logical :: use_psom=.false.` -- the translator skips declarations, initialisers included
             head, rest = code.split("\n", 1)
             code = head + "\n    use_psom = False\n" + rest
@@ -241,6 +251,8 @@ def run_case(name):
     cites = {}
     for kind, nm in (("subroutine", "advect_tracer_sweby_all"), ("function", "advect_tracer_mdfl_sweby"),
                      ("function", "advect_tracer_mdfl_sweby_test"),
+                     ("subroutine", "ppm_limit_cw84"), ("subroutine", "ppm_limit_ifc"), ("subroutine", "ppm_limit_sh"),
+                     ("function", "advect_tracer_mdppm"),
                      ("function", "horz_advect_tracer_upwind"), ("function", "vert_advect_tracer_upwind"),
                      ("function", "horz_advect_tracer_quicker"), ("function", "vert_advect_tracer_quicker"),
                      ("subroutine", "compute_adv_diss"),
@@ -266,6 +278,15 @@ def run_case(name):
     code = "\n".join(l for l in code.split("\n") if not re.match(r"\s*(mass_mdfl|tracermass_mdfl)", l))
     exec(compile(code, f"<OTA:{a}-{z} mdfl_init>", "exec"), env)
     out["tmask_mdfl"] = env["tmask_mdfl"].a.copy()
+
+    # ---- mdppm_init: halo-4 mask (OTA:1714-1726) ----
+    f0, l0 = find_routine(src, "subroutine", "mdppm_init")
+    a = find_line(src, r"^\s*tmask_mdppm\s*=\s*0\.0", f0)
+    z = find_line(src, r"call mpp_update_domains\(tmask_mdppm", a)
+    code = translate_block(src, a, z, array_names=arrays)
+    code = "\n".join(l for l in code.split("\n") if not re.match(r"\s*(mass_mdppm|tracermass_mdppm)", l))
+    exec(compile(code, f"<OTA:{a}-{z} mdppm_init>", "exec"), env)
+    out["tmask_mdppm"] = env["tmask_mdppm"].a.copy()
 
     T_prog = env["T_prog"]
     ntr = len(T_prog.items)
@@ -303,13 +324,15 @@ def run_case(name):
 
     arms = [("upwind", "ADVECT_UPWIND", False), ("quicker", "ADVECT_QUICKER", False), ("quicker_lim", "ADVECT_QUICKER", True),
             ("mdfl_sweby", "ADVECT_MDFL_SWEBY", False), ("dst_linear", "ADVECT_DST_LINEAR", False),
-            ("mdfl_sweby_test", "ADVECT_MDFL_SWEBY_TEST", False), ("dst_linear_test", "ADVECT_DST_LINEAR_TEST", False)]
+            ("mdfl_sweby_test", "ADVECT_MDFL_SWEBY_TEST", False), ("dst_linear_test", "ADVECT_DST_LINEAR_TEST", False),
+            ("mdppm_cw84", "ADVECT_MDPPM", False), ("mdppm_ifc", "ADVECT_MDPPM", False), ("mdppm_sh", "ADVECT_MDPPM", False)]
     for tag, scheme, lim in arms:
         t0 = time.time()
         reset()
         env["limit_with_upwind"] = lim
-        n = min(2, ntr) if tag in ("quicker_lim", "dst_linear_test") else 1
+        n = min(2, ntr) if tag in ("quicker_lim", "dst_linear_test", "mdppm_ifc") else 1
         tr = T_prog(n)
+        tr.ppm_hlimiter = tr.ppm_vlimiter = {"mdppm_ifc": 2, "mdppm_sh": 3}.get(tag, 1)
         tr.conversion = 3992.1 if n == 1 else 1.0     # only compute_adv_diss output is kept from the diagnostics of the arms
         tr.horz_advect_scheme = tr.vert_advect_scheme = env[scheme]
         env["horz_advect_tracer"](env["Time"], env["Adv_vel"], env["Thickness"], env["Dens"], T_prog, tr, n, s.dtime)
@@ -317,6 +340,8 @@ def run_case(name):
         out[f"{tag}.horz.th_tendency"] = tr.th_tendency.a.copy()
         out[f"{tag}.flux_x"] = env["flux_x"].a.copy()
         out[f"{tag}.flux_y"] = env["flux_y"].a.copy()
+        if tag.startswith("mdppm"):
+            out[f"{tag}.tracer_mdppm"] = env["tracer_mdppm"].a.copy()
         if tag.endswith("_test"):   # the three running fields after the y sweep (compute domain is what matters)
             for nm in ("tracer_mdfl", "tracermass_mdfl", "mass_mdfl"):
                 out[f"{tag}.{nm}"] = env[nm].a.copy()

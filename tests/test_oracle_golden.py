@@ -95,7 +95,31 @@ def test_mdfl_sweby_test_variant(name, tag, sl):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test"])
+@pytest.mark.parametrize("tag,limiter", [("mdppm_cw84", 1), ("mdppm_ifc", 2), ("mdppm_sh", 3)])
+def test_mdppm(name, tag, limiter):
+    """advect_tracer_mdppm (OTA:5990-6494) with the three edge-value limiters (OTA:6510-6657), halo 4"""
+    import ctypes as C
+    from oracle.oracle import _ptr
+    b, gold, _ = load_golden(name)
+    _, o = _oracle(b)
+    o.mdppm_init()
+    assert_bit_equal(o.m4[0], gold["tmask_mdppm"], "tmask_mdppm")
+    n = int(gold[f"{tag}.tracer"])
+    out = o.mdppm([b.T[n - 1].numpy()], b.spec.dtime, limiter)
+    assert_bit_equal(out["wrk1"][0], gold[f"{tag}.horz.wrk1"], "wrk1")
+    th = b.th_tendency[n - 1].numpy().copy()
+    o.L.orc_accumulate(C.byref(o.blocks[0].c), _ptr(out["wrk1"][0]), _ptr(th))
+    assert_bit_equal(th, gold[f"{tag}.horz.th_tendency"], "th_tendency")
+    assert_bit_equal(out["flux_x"][0], gold[f"{tag}.flux_x"], "flux_x")
+    assert_bit_equal(out["flux_y"][0], gold[f"{tag}.flux_y"], "flux_y")
+    assert_bit_equal(out["flux_z"][0][:, 1:-1, 1:-1], gold[f"{tag}.flux_z"][:, 1:-1, 1:-1], "flux_z")
+    assert_bit_equal(out["tracer"][0][:, 4:-4, 4:-4], gold[f"{tag}.tracer_mdppm"][:, 4:-4, 4:-4], "tracer_mdppm")
+    assert not gold[f"{tag}.vert.wrk1"].any()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test",
+                                 "mdppm_cw84", "mdppm_ifc", "mdppm_sh"])
 def test_compute_adv_diss(name, tag):
     """compute_adv_diss (OTA:7547-7712): the scheme applied to the squared tracer, then the dissipation formula"""
     b, gold, _ = load_golden(name)

@@ -42,6 +42,7 @@ extern "C" {
 /* scheme ids == ocean_parameters.F90:149-163 */
 #define MOM5ADV_ADVECT_UPWIND 1
 #define MOM5ADV_ADVECT_QUICKER 5
+#define MOM5ADV_ADVECT_MDPPM 8
 #define MOM5ADV_ADVECT_MDFL_SWEBY 9
 #define MOM5ADV_ADVECT_DST_LINEAR 10
 #define MOM5ADV_ADVECT_MDFL_SWEBY_TEST 12
@@ -105,7 +106,8 @@ int mom5adv_sweby_all_dev(mom5adv_handle h, int ntr, double dtime,
                           double *const *adv_x, double *const *adv_y, double *const *adv_z, void *stream);
 
 /* ---- horz_advect_tracer (OTA:1898-2083), one tracer, advect_sweby_all = .false. -----------------------
- * scheme: UPWIND (OTA:2238-2294), QUICKER (OTA:2538-2653), MDFL_SWEBY / DST_LINEAR (OTA:3806-4066).
+ * scheme: UPWIND (OTA:2238-2294), QUICKER (OTA:2538-2653), MDFL_SWEBY / DST_LINEAR (OTA:3806-4066),
+ * MDFL_SWEBY_TEST / DST_LINEAR_TEST (OTA:3469-3746), MDPPM (OTA:5990-6494; limiter via mom5adv_set_ppm_limiters).
  * wrk1_out (= Tracer%wrk1) := -scheme(...) on the compute domain, 0 on the halo ring;
  * th_tendency += wrk1_out on the compute domain (OTA:1990-1996).  flux_x/flux_y/flux_z may be NULL.
  * T_tau and tmask_limit are read by QUICKER only (tmask_limit only if limit_with_upwind != 0).           */
@@ -156,6 +158,12 @@ int mom5adv_sweby_all_step_dev(mom5adv_handle h, int ntr, double dtime, const do
 int mom5adv_continuity_dev(mom5adv_handle h, const double *uhrho_et, const double *vhrho_nt,
                            const double *rho_dzt_tendency, const double *mass_source, double *wrho_bt,
                            double *diverge_t, void *stream);
+
+/* Tracer%ppm_hlimiter / Tracer%ppm_vlimiter of the tracer the next ADVECT_MDPPM calls advect (field-table entries,
+ * ocean_tracer.F90:1006,1051; defaults 1): 1 = Colella-Woodward 1984, 2 = Lin's improved full constraint, 3 = Suresh-Huynh
+ * 1997 (ppm_limit_cw84 / _ifc / _sh, OTA:6510-6657).  advect_tracer_mdppm reads ppm_hlimiter in all three directions
+ * (OTA:6137,6263,6399); any other value makes the scheme fail as the reference does (OTA:6146-6148).                 */
+int mom5adv_set_ppm_limiters(mom5adv_handle h, int ppm_hlimiter, int ppm_vlimiter);
 
 /* ---- diagnostics producers ------------------------------------------------------
  * mom5adv_adv_diss_dev: compute_adv_diss (OTA:7547-7712), called from vert_advect_tracer's tail (OTA:2221-2223): the

@@ -24,13 +24,14 @@ from ._lib import Grid, check, dp, dpp
 
 ADVECT_UPWIND = 1            # ocean_parameters.F90:149-163
 ADVECT_QUICKER = 5
+ADVECT_MDPPM = 8
 ADVECT_MDFL_SWEBY = 9
 ADVECT_DST_LINEAR = 10
 ADVECT_MDFL_SWEBY_TEST = 12
 ADVECT_DST_LINEAR_TEST = 14
 SCHEME_IDS = {"upwind": ADVECT_UPWIND, "quicker": ADVECT_QUICKER, "mdfl_sweby": ADVECT_MDFL_SWEBY,
               "dst_linear": ADVECT_DST_LINEAR, "mdfl_sweby_test": ADVECT_MDFL_SWEBY_TEST,
-              "dst_linear_test": ADVECT_DST_LINEAR_TEST}
+              "dst_linear_test": ADVECT_DST_LINEAR_TEST, "mdppm": ADVECT_MDPPM}
 
 
 def _is_torch(a) -> bool:
@@ -182,6 +183,10 @@ class TracerAdvect:
     def continuity(self, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tendency=None, mass_source=None, diverge_t=None):
         check(self.L.mom5adv_continuity_dev(self.handle, _ptr(uhrho_et), _ptr(vhrho_nt), _ptr(rho_dzt_tendency), _ptr(mass_source),
                                             _ptr(wrho_bt), _ptr(diverge_t), _cur_stream()), "continuity_dev")
+
+    def set_ppm_limiters(self, ppm_hlimiter: int = 1, ppm_vlimiter: int = 1):
+        """Tracer%ppm_hlimiter / ppm_vlimiter of the tracer the next ADVECT_MDPPM calls advect (1 cw84, 2 ifc, 3 sh)"""
+        check(self.L.mom5adv_set_ppm_limiters(self.handle, int(ppm_hlimiter), int(ppm_vlimiter)), "set_ppm_limiters")
 
     # ---- diagnostics producers: compute_adv_diss (OTA:7547-7712), z-integrated fluxes (OTA:4317-4326) ----
     def adv_diss(self, horz_scheme: int, vert_scheme: int, T_tau, advect_tendency, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tau,

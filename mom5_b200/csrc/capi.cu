@@ -17,6 +17,7 @@
 #include "sweby_kernels.cuh"
 #include "sweby_fused.cuh"
 #include "sweby_test_kernels.cuh"
+#include "mdppm_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -94,6 +95,10 @@ struct mom5adv_ctx {
     QuickW qw{};                       // quicker weights (device)
     std::vector<double *> tmA, tmB;    // h2 scratch per tracer
     double *st_ms = 0;                 // mass_mdfl of advect_tracer_mdfl_sweby_test (h2 scratch, allocated on first use)
+    double *pp_fz = 0;                 // MDPPM: flux_z work array when the caller does not want it
+    double *pp_tr = 0, *pp_m4 = 0, *pp_da = 0;   // MDPPM: tracer_mdppm, tmask_mdppm, slope scratch (h4, allocated on first use)
+    HaloPlan plan4[4];                 // halo-4 updates (Dom_mdppm, OTA:1706), indexed by flags
+    int ppm_hlimiter = 1, ppm_vlimiter = 1;      // Tracer%ppm_hlimiter / ppm_vlimiter defaults (ocean_types.F90:1018-1019)
     // halo machinery
     HaloPlan plan[4];                  // indexed by flags (1 = X, 2 = Y, 3 = XY)
     HaloPlan plan1;                    // halo-1 full update of data-domain arrays (field(taup1), OM:1903-1911)
@@ -346,7 +351,7 @@ extern "C" int mom5adv_comm_destroy(mom5adv_comm c)
 template <int LAYOUT>
 static int halo_update_l(mom5adv_ctx *h, double *const *fields, int nf, int flags, cudaStream_t st)
 {
-    const HaloPlan &P = (LAYOUT == 0) ? h->plan[flags & 3] : h->plan1;
+    const HaloPlan &P = (LAYOUT == 0) ? h->plan[flags & 3] : (LAYOUT == 1) ? h->plan1 : h->plan4[flags & 3];
     const int nk = h->g.nk;
     for (int f0 = 0; f0 < nf; f0 += HALO_MAXF) {
         const int nfc = std::min(HALO_MAXF, nf - f0);
@@ -518,6 +523,7 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     g.nxd = g.ni + 2; g.nyd = g.nj + 2; g.slab = (long long)g.nxd * g.nyd;
     g.tpitch = ((g.ni + TOFF + 3) + 15) / 16 * 16; g.tslab = (long long)g.tpitch * (g.nj + 4);
     g.mpitch = g.tpitch; g.mslab = g.tslab;
+    g.p4 = g.ni + 8; g.s4 = (long long)g.p4 * (g.nj + 8);
     if ((unsigned long long)g.tslab * (unsigned long long)g.nk >= (1ull << 32) || (unsigned long long)g.slab * (unsigned long long)(g.nk + 2) >= (1ull << 32)) {
         set_error("mom5adv_init: local block too large (the kernels index with 32-bit element offsets: < 2^32 elements per array)");
         delete h;
@@ -553,6 +559,7 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     DomInfo D{h->ni_g, h->nj_g, h->px, h->py, h->cyclic_x, h->cyclic_y, h->tripolar, &h->ibeg, &h->iend, &h->jbeg, &h->jend};
     for (int f = 1; f <= 3; f++) build_plan(D, h->rank, f, 2, h->plan[f]);
     build_plan(D, h->rank, 3, 1, h->plan1);
+    for (int f = 1; f <= 3; f++) build_plan(D, h->rank, f, 4, h->plan4[f]);
 
     // tmask_mdfl == tmask_quick: compute domain := Grd%tmask, full halo-2 update (OTA:1668-1675, 1478-1487), stored as u8
     cudaStream_t st = h->stream;
@@ -579,7 +586,7 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
 {
     if (!h) return 0;
     cudaDeviceSynchronize();
-    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms})
+    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms, h->pp_tr, h->pp_m4, h->pp_da, h->pp_fz})
         if (p) cudaFree(p);
     for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
         if (p) cudaFree(p);
@@ -1239,6 +1246,56 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    case MOM5ADV_ADVECT_MDPPM: {
+        if (!w || !rho) { set_error("mom5adv_horz_dev: mdppm needs wrho_bt and rho_dzt"); return MOM5ADV_EINVAL; }
+        if (h->ppm_hlimiter < 1 || h->ppm_hlimiter > 3) {   // OTA:6146-6148
+            set_error("mom5adv_horz_dev: must choose ppm_hlimiter=1,2 or 3");
+            return MOM5ADV_EINVAL;
+        }
+        int rc;
+        const size_t n4 = (size_t)g.s4 * g.nk;
+        if (!h->pp_tr) {
+            CUDA_TRY(cudaMalloc(&h->pp_tr, n4 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->pp_da, n4 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->pp_m4, n4 * sizeof(double)));
+            // mdppm_init (OTA:1714-1726): tmask_mdppm = 0; compute domain := Grd%tmask; full halo-4 update
+            CUDA_TRY(cudaMemsetAsync(h->pp_m4, 0, n4 * sizeof(double), st));
+            LAUNCH(h, k_d1_to_h4, dim3((g.ni + 127) / 128, g.nj, g.nk), 128, 0, st, g, h->tmask, h->pp_m4);
+            double *m1[1] = {h->pp_m4};
+            if ((rc = halo_update_l<2>(h, m1, 1, 3, st))) return rc;
+        }
+        PPMArgs a{};
+        a.T = Tm1; a.u = u; a.v = v; a.w = w; a.rho = rho; a.m4 = h->pp_m4; a.tmask = h->tmask;
+        a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
+        a.tr = h->pp_tr; a.da = h->pp_da; a.fx = fx; a.fy = fy; a.fz = fz; a.th = th; a.wrk1 = wrk1;
+        a.dtime = dtime; a.limiter = h->ppm_hlimiter;
+        if (!a.fx && (rc = mirror(h, 0, &a.fx))) return rc;    // the reference's module-level flux work arrays
+        if (!a.fy && (rc = mirror(h, 1, &a.fy))) return rc;
+        if (!a.fz) {
+            if (!h->pp_fz) CUDA_TRY(cudaMalloc(&h->pp_fz, n3(h) * sizeof(double)));
+            a.fz = h->pp_fz;
+        }
+        CUDA_TRY(cudaMemsetAsync(a.tr, 0, n4 * sizeof(double), st));       // tracer_mdppm = 0.0 (OTA:6022)
+        CUDA_TRY(cudaMemsetAsync(a.fx, 0, n3(h) * sizeof(double), st));    // flux_x = flux_y = 0.0 (OTA:6023-6024)
+        CUDA_TRY(cudaMemsetAsync(a.fy, 0, n3(h) * sizeof(double), st));
+        double *wz[1] = {wrk1}, *t1[1] = {a.tr};
+        zero_rings(h, wz, 1, st);                                           // Tracer%wrk1 = 0 on the data domain (OTA:1925-1931)
+        const int nbx = (g.ni + 127) / 128;
+        const dim3 cells(nbx, g.nj, g.nk);
+        LAUNCH(h, k_ppm_zslope, cells, 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_zflux, cells, 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_zupd, cells, 128, 0, st, g, a);
+        if ((rc = halo_update_l<2>(h, t1, 1, 1, st))) return rc;           // XUPDATE, halo 4 (OTA:6201)
+        LAUNCH(h, k_ppm_hslope<0>, dim3((g.ni + 4 + 127) / 128, g.nj, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_hflux<0>, dim3((g.ni + 1 + 127) / 128, g.nj, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_xupd, cells, 128, 0, st, g, a);
+        if ((rc = halo_update_l<2>(h, t1, 1, 2, st))) return rc;           // YUPDATE (OTA:6333)
+        LAUNCH(h, k_ppm_hslope<1>, dim3(nbx, g.nj + 4, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_hflux<1>, dim3(nbx, g.nj + 1, g.nk), 128, 0, st, g, a);
+        LAUNCH(h, k_ppm_yupd, cells, 128, 0, st, g, a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     case MOM5ADV_ADVECT_UPWIND: {
         double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
         int rc;
@@ -1279,6 +1336,7 @@ extern "C" int mom5adv_vert_dev(mom5adv_handle h, int scheme, const double *Tm1,
     switch (scheme) {
     case MOM5ADV_ADVECT_MDFL_SWEBY:
     case MOM5ADV_ADVECT_DST_LINEAR:
+    case MOM5ADV_ADVECT_MDPPM:
     case MOM5ADV_ADVECT_MDFL_SWEBY_TEST:
     case MOM5ADV_ADVECT_DST_LINEAR_TEST:   // three-dimensional schemes: wrk1 = 0, th unchanged (OTA:2116-2122, 2147-2155)
         CUDA_TRY(cudaMemsetAsync(wrk1, 0, n3(h) * sizeof(double), st));
@@ -1370,7 +1428,7 @@ extern "C" int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_
     LAUNCH(h, k_square, 148 * 8, 256, 0, st, N, T_tau, sq);
     switch (horz_scheme) {   // OTA:7583-7626: the operator acts on the squared tracer at BOTH time levels
     case MOM5ADV_ADVECT_UPWIND: case MOM5ADV_ADVECT_QUICKER: case MOM5ADV_ADVECT_MDFL_SWEBY: case MOM5ADV_ADVECT_DST_LINEAR:
-    case MOM5ADV_ADVECT_DST_LINEAR_TEST:
+    case MOM5ADV_ADVECT_DST_LINEAR_TEST: case MOM5ADV_ADVECT_MDPPM:
         if ((rc = mom5adv_horz_dev(h, horz_scheme, dtime, sq, sq, tlimit, limit_with_upwind, u, v, w, rho_tau, thd, w2, nullptr, nullptr, nullptr, st))) return rc;
         break;
     case MOM5ADV_ADVECT_MDFL_SWEBY_TEST:   // has no arm in compute_adv_diss's select: wrk2 stays 0
@@ -1382,7 +1440,7 @@ extern "C" int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_
     }
     switch (vert_scheme) {   // OTA:7628-7662
     case MOM5ADV_ADVECT_UPWIND: case MOM5ADV_ADVECT_QUICKER: case MOM5ADV_ADVECT_MDFL_SWEBY: case MOM5ADV_ADVECT_DST_LINEAR:
-    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST: case MOM5ADV_ADVECT_DST_LINEAR_TEST:
+    case MOM5ADV_ADVECT_MDFL_SWEBY_TEST: case MOM5ADV_ADVECT_DST_LINEAR_TEST: case MOM5ADV_ADVECT_MDPPM:
         if ((rc = mom5adv_vert_dev(h, vert_scheme, sq, sq, tlimit, w, thd, w3, nullptr, st))) return rc;
         break;
     default:
@@ -1392,6 +1450,14 @@ extern "C" int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_
     DissArgs a{rho_tau, rho_taup1, T_tau, advect_tendency, w2, w3, t2_tendency, adv_diss, dtime, 1.0 / dtime, conversion};
     LAUNCH(h, k_adv_diss, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, a);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mom5adv_set_ppm_limiters(mom5adv_handle h, int ppm_hlimiter, int ppm_vlimiter)
+{
+    if (!h) { set_error("mom5adv_set_ppm_limiters: null handle"); return MOM5ADV_EINVAL; }
+    h->ppm_hlimiter = ppm_hlimiter;   // validated where the reference validates it: inside the scheme (OTA:6137-6148)
+    h->ppm_vlimiter = ppm_vlimiter;
     return 0;
 }
 

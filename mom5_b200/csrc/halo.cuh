@@ -36,9 +36,13 @@ struct CopyArgs {
 };
 
 // mode 0: local copy (src rect -> dst rect, same rank); 1: pack (src rect -> buf); 2: unpack (buf -> dst rect)
-// LAYOUT 0: h2 scratch fields (halo 2, t3 indexing); LAYOUT 1: caller's data-domain arrays (halo 1, d3 indexing)
+// LAYOUT 0: h2 scratch fields (halo 2, t3 indexing); LAYOUT 1: caller's data-domain arrays (halo 1, d3 indexing);
+// LAYOUT 2: h4 scratch fields (halo 4, q3 indexing; MDPPM)
 template <int LAYOUT>
-__device__ __forceinline__ size_t halo_idx(const Geom &g, int i, int j, int k) { return LAYOUT == 0 ? t3(g, i, j, k) : d3(g, i, j, k); }
+__device__ __forceinline__ size_t halo_idx(const Geom &g, int i, int j, int k)
+{
+    return LAYOUT == 0 ? t3(g, i, j, k) : LAYOUT == 1 ? d3(g, i, j, k) : q3(g, i, j, k);
+}
 
 template <int MODE, int LAYOUT>
 __global__ void k_halo(const Geom g, const CopyArgs a)

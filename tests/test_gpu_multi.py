@@ -25,7 +25,7 @@ def _worker(rank, world, port, case, over, px, py, outdir):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    from mom5_b200.api import ADVECT_MDFL_SWEBY, ADVECT_MDFL_SWEBY_TEST, ADVECT_QUICKER, Communicator, TracerAdvect
+    from mom5_b200.api import ADVECT_MDFL_SWEBY, ADVECT_MDFL_SWEBY_TEST, ADVECT_MDPPM, ADVECT_QUICKER, Communicator, TracerAdvect
     from mom5_b200.synthetic import make_case
     g = make_case(case, **over)
     dec = g.s.decomposition(px, py)
@@ -58,6 +58,11 @@ def _worker(rank, world, port, case, over, px, py, outdir):
     w3 = torch.empty_like(th3)
     adv.horz_advect_tracer(ADVECT_MDFL_SWEBY_TEST, T[0], th3, w3, u, v, g.s.dtime, wrho_bt=w, rho_dzt=rho)
     res["sweby_test"] = w3.cpu().numpy()
+    th4 = b.th_tendency[0].cuda().clone()   # MDPPM: halo-4 strips
+    w4 = torch.empty_like(th4)
+    adv.set_ppm_limiters(3)
+    adv.horz_advect_tracer(ADVECT_MDPPM, T[0], th4, w4, u, v, g.s.dtime, wrho_bt=w, rho_dzt=rho)
+    res["mdppm"] = w4.cpu().numpy()
     torch.cuda.synchronize()
     for n in range(len(T)):
         res[f"th{n}"] = th[n].cpu().numpy()
@@ -83,6 +88,7 @@ def _check(tmp_path, case, over, px, py):
     th = [[t.numpy().copy() for t in gb.th_tendency]]
     ref = o.sweby_all([[t.numpy() for t in gb.T]], th, g.s.dtime)
     mdfl = o.mdfl_sweby([gb.T[0].numpy()], g.s.dtime, 1.0)["wrk1"][0]
+    ppm = o.mdppm([gb.T[0].numpy()], g.s.dtime, 3)["wrk1"][0]
     stest = o.sweby_test([gb.T[0].numpy()], g.s.dtime, 1.0)["wrk1"][0]
     quick = o.horz_quicker([gb.T[0].numpy()], [gb.T_tau[0].numpy()], [gb.tmask_limit[0].numpy()], False)["wrk1"][0]
     for r in range(world):
@@ -92,6 +98,7 @@ def _check(tmp_path, case, over, px, py):
         cmp = [(f"th{n}", th[0][n]) for n in range(len(gb.T))] + [(f"adv{n}", ref["adv"][0][n]) for n in range(len(gb.T))]
         cmp.append(("mdfl", mdfl))
         cmp.append(("sweby_test", stest))
+        cmp.append(("mdppm", ppm))
         if "quicker" in z.files:
             cmp.append(("quicker", quick))
         for nm, full in cmp:

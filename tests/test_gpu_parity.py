@@ -97,13 +97,16 @@ def test_sweby_all_host_pointer_pipelines_vs_oracle(case, over, banded, monkeypa
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("tag", ["mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test", "quicker", "quicker_lim", "upwind"])
+@pytest.mark.parametrize("tag", ["mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test", "mdppm_cw84", "mdppm_ifc", "mdppm_sh",
+                                 "quicker", "quicker_lim", "upwind"])
 def test_dispatcher_arms_vs_reference_golden(name, tag):
     from mom5_b200.api import SCHEME_IDS, TracerAdvect
     b, gold, _ = load_golden(name)
     n = int(gold[f"{tag}.tracer"]) - 1
-    scheme = SCHEME_IDS[tag.replace("_lim", "")]
+    scheme = SCHEME_IDS[tag.replace("_lim", "").split("_cw84")[0].split("_ifc")[0].split("_sh")[0]]
     adv = TracerAdvect(b, ntracers_max=1, limit_with_upwind=(tag == "quicker_lim"))
+    if tag.startswith("mdppm"):
+        adv.set_ppm_limiters({"mdppm_cw84": 1, "mdppm_ifc": 2, "mdppm_sh": 3}[tag])
     Tm1, Tt, tl = _dev(b.T[n]), _dev(b.T_tau[n]), _dev(b.tmask_limit[n])
     th = _dev(b.th_tendency[n]).clone()
     wrk1 = torch.full_like(th, -777.0)
@@ -151,6 +154,48 @@ def test_sweby_test_variant_vs_oracle(case, over, tag, sl, sweep_mode):
     assert_bit_equal(fy, ref["flux_y"][0], "flux_y")
     assert_bit_equal(fz[:, 1:-1, 1:-1], ref["flux_z"][0][:, 1:-1, 1:-1], "flux_z")
     assert float(wrk1.abs().max()) > 0
+    adv.close()
+
+
+@pytest.mark.parametrize("case,over", [("mini_tripolar", {}), ("mini_torus", {}), ("global_1deg", dict(ni=130, nj=70, nk=50, ntr=2, cfl=0.9)),
+                                       ("gyre", dict(ni=96, nj=80, nk=20, ntr=2))])
+@pytest.mark.parametrize("limiter", [1, 2, 3])
+def test_mdppm_vs_oracle(case, over, limiter, sweep_mode):
+    """advect_tracer_mdppm (OTA:5990-6494) on larger seeded cases, all three limiters; also through the host-pointer entry"""
+    from mom5_b200.api import ADVECT_MDPPM, TracerAdvect
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    if sweep_mode == "unfused":
+        pytest.skip("not a Sweby-driver test")
+    g = make_case(case, **over)
+    b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    ref = o.mdppm([b.T[0].numpy()], g.s.dtime, limiter)
+    adv = TracerAdvect(b, ntracers_max=1)
+    adv.set_ppm_limiters(limiter)
+    th0 = _dev(b.th_tendency[0])
+    th = th0.clone()
+    wrk1 = torch.full_like(th, -777.0)
+    fx, fy, fz = torch.full_like(th, 5.0), torch.full_like(th, 5.0), torch.zeros_like(th)
+    adv.horz_advect_tracer(ADVECT_MDPPM, _dev(b.T[0]), th, wrk1, _dev(b.uhrho_et), _dev(b.vhrho_nt), g.s.dtime,
+                           wrho_bt=_dev(b.wrho_bt), rho_dzt=_dev(b.rho_dzt), flux_x=fx, flux_y=fy, flux_z=fz)
+    torch.cuda.synchronize()
+    assert_bit_equal(wrk1, ref["wrk1"][0], f"{case} mdppm[{limiter}] wrk1")
+    assert_bit_equal(th[:, 1:-1, 1:-1], (b.th_tendency[0].numpy() + ref["wrk1"][0])[:, 1:-1, 1:-1], "th")
+    assert_bit_equal(fx, ref["flux_x"][0], "flux_x")
+    assert_bit_equal(fy, ref["flux_y"][0], "flux_y")
+    assert_bit_equal(fz[:, 1:-1, 1:-1], ref["flux_z"][0][:, 1:-1, 1:-1], "flux_z")
+    # host arrays, no flux diagnostics wanted (internal flux work arrays)
+    th_h = b.th_tendency[0].numpy().copy()
+    w_h = np.full_like(th_h, -777.0)
+    adv.horz_advect_tracer(ADVECT_MDPPM, b.T[0].numpy(), th_h, w_h, b.uhrho_et.numpy(), b.vhrho_nt.numpy(), g.s.dtime,
+                           wrho_bt=b.wrho_bt.numpy(), rho_dzt=b.rho_dzt.numpy())
+    assert_bit_equal(w_h, ref["wrk1"][0], "host-pointer wrk1")
+    adv.set_ppm_limiters(4)
+    from mom5_b200._lib import Mom5AdvError
+    with pytest.raises(Mom5AdvError, match="ppm_hlimiter"):
+        adv.horz_advect_tracer(ADVECT_MDPPM, _dev(b.T[0]), th, wrk1, _dev(b.uhrho_et), _dev(b.vhrho_nt), g.s.dtime,
+                               wrho_bt=_dev(b.wrho_bt), rho_dzt=_dev(b.rho_dzt))
     adv.close()
 
 
@@ -281,14 +326,17 @@ def test_advection_only_time_stepping(case, fused_update, sweep_mode):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test"])
+@pytest.mark.parametrize("tag", ["upwind", "quicker", "quicker_lim", "mdfl_sweby", "dst_linear", "mdfl_sweby_test", "dst_linear_test",
+                                 "mdppm_cw84", "mdppm_sh"])
 def test_adv_diss_vs_reference_golden(name, tag, sweep_mode):
     """compute_adv_diss (OTA:7547-7712) on device: operators on the squared tracer + the dissipation formula"""
     from mom5_b200.api import SCHEME_IDS, TracerAdvect
     b, gold, _ = load_golden(name)
     n = int(gold[f"{tag}.tracer"]) - 1
-    scheme = SCHEME_IDS[tag.replace("_lim", "")]
+    scheme = SCHEME_IDS[tag.replace("_lim", "").split("_cw84")[0].split("_sh")[0]]
     adv = TracerAdvect(b, ntracers_max=1, limit_with_upwind=(tag == "quicker_lim"))
+    if tag.startswith("mdppm"):
+        adv.set_ppm_limiters({"mdppm_cw84": 1, "mdppm_sh": 3}[tag])
     rho = _dev(b.rho_dzt)
     diss = torch.full_like(rho, -777.0)
     t2 = torch.full_like(rho, -777.0)

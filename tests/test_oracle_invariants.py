@@ -50,6 +50,7 @@ def test_decomposition_invariance_other_schemes(case):
         res = dict(
             mdfl=o.mdfl_sweby(Tm1, g.s.dtime, 1.0)["wrk1"], dst=o.mdfl_sweby(Tm1, g.s.dtime, 0.0)["wrk1"],
             mdflt=o.sweby_test(Tm1, g.s.dtime, 1.0)["wrk1"], dstt=o.sweby_test(Tm1, g.s.dtime, 0.0)["wrk1"],
+            ppm1=o.mdppm(Tm1, g.s.dtime, 1)["wrk1"], ppm2=o.mdppm(Tm1, g.s.dtime, 2)["wrk1"], ppm3=o.mdppm(Tm1, g.s.dtime, 3)["wrk1"],
             qh=o.horz_quicker(Tm1, Tt, tl, False)["wrk1"], qhl=o.horz_quicker(Tm1, Tt, tl, True)["wrk1"],
             qv=o.vert_quicker(Tm1, Tt, tl)["wrk1"], uh=o.horz_upwind(Tm1)["wrk1"], uv=o.vert_upwind(Tm1)["wrk1"])
         for k, v in res.items():

@@ -23,7 +23,7 @@
 namespace mom5 {
 
 // scheme ids, ocean_parameters.F90:149-163
-enum : int { ADVECT_UPWIND = 1, ADVECT_QUICKER = 5, ADVECT_MDFL_SWEBY = 9, ADVECT_DST_LINEAR = 10,
+enum : int { ADVECT_UPWIND = 1, ADVECT_QUICKER = 5, ADVECT_MDPPM = 8, ADVECT_MDFL_SWEBY = 9, ADVECT_DST_LINEAR = 10,
              ADVECT_MDFL_SWEBY_TEST = 12, ADVECT_DST_LINEAR_TEST = 14 };
 
 // ocean_time_type (ocean_types.F90:937-947): 1-based time-level indices into field(:,:,:,1:3)
@@ -66,6 +66,7 @@ struct ocean_prog_tracer_type {
     double *wrk1;                         // (isd:ied, jsd:jed, nk)
     const double *tmask_limit = nullptr;  // (isd:ied, jsd:jed, nk)
     int horz_advect_scheme = ADVECT_MDFL_SWEBY, vert_advect_scheme = ADVECT_MDFL_SWEBY;
+    int ppm_hlimiter = 1, ppm_vlimiter = 1;   // ocean_types.F90:1018-1019 (ADVECT_MDPPM)
 };
 
 // ocean_tracer_advect_nml (OTA:483-495), the switches that change this path
@@ -108,9 +109,11 @@ public:
         if (!nml_.advect_sweby_all) {                                              // OTA:1923-2075
             switch (Tracer.horz_advect_scheme) {
             case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR:
-            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: break;
+            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: case ADVECT_MDPPM: break;
             default: throw std::runtime_error("==>Error from ocean_tracer_advect_mod (horz_advect_tracer): chose invalid horz advection scheme");
             }
+            if (Tracer.horz_advect_scheme == ADVECT_MDPPM)
+                check(mom5adv_set_ppm_limiters(h_, Tracer.ppm_hlimiter, Tracer.ppm_vlimiter), "ppm limiters");
             check(mom5adv_horz(h_, Tracer.horz_advect_scheme, dtime, level(Tracer.field, Time.taum1), level(Tracer.field, Time.tau),
                                Tracer.tmask_limit, nml_.limit_with_upwind, Adv_vel.uhrho_et, Adv_vel.vhrho_nt, Adv_vel.wrho_bt,
                                rho_tau, Tracer.th_tendency, Tracer.wrk1, nullptr, nullptr, nullptr),
@@ -137,7 +140,7 @@ public:
         if (nml_.advect_sweby_all) return;                                         // OTA:2114
         switch (Tracer.vert_advect_scheme) {
         case ADVECT_UPWIND: case ADVECT_QUICKER: case ADVECT_MDFL_SWEBY: case ADVECT_DST_LINEAR:
-            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: break;
+            case ADVECT_MDFL_SWEBY_TEST: case ADVECT_DST_LINEAR_TEST: case ADVECT_MDPPM: break;
         default: throw std::runtime_error("==>Error from ocean_tracer_advect_mod (vert_advect_tracer): invalid advection scheme chosen");
         }
         check(mom5adv_vert(h_, Tracer.vert_advect_scheme, level(Tracer.field, Time.taum1), level(Tracer.field, Time.tau),

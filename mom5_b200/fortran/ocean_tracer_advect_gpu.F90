@@ -14,6 +14,7 @@ module ocean_tracer_advect_gpu_mod
   use ocean_types_mod,  only: ocean_grid_type, ocean_domain_type, ocean_prog_tracer_type, &
                               ocean_adv_vel_type, ocean_thickness_type, ocean_time_type
   use mpp_mod,          only: mpp_error, FATAL, mpp_pe, mpp_npes, mpp_root_pe, mpp_broadcast
+  use ocean_parameters_mod, only: ADVECT_MDPPM
   implicit none
   private
   public :: gpu_tracer_advect_init, gpu_advect_tracer_sweby_all, gpu_horz_advect_tracer, gpu_vert_advect_tracer, &
@@ -77,6 +78,12 @@ module ocean_tracer_advect_gpu_mod
        type(c_ptr), value :: Tm1, Tt, tlimit, u, v, w, rho, th, wrk1, fx, fy, fz
        integer(c_int) :: rc
      end function
+     function mom5adv_set_ppm_limiters(handle, ppm_hlimiter, ppm_vlimiter) bind(C, name='mom5adv_set_ppm_limiters') result(rc)
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: handle
+       integer(c_int), value :: ppm_hlimiter, ppm_vlimiter
+       integer(c_int)        :: rc
+     end function mom5adv_set_ppm_limiters
      function mom5adv_vert(handle, scheme, Tm1, Tt, tlimit, w, th, wrk1, fz) bind(C, name='mom5adv_vert') result(rc)
        import :: c_int, c_ptr
        type(c_ptr), value :: handle
@@ -170,6 +177,9 @@ contains
     real, dimension(:,:,:),       intent(inout), target :: flux_x, flux_y, flux_z   ! the module work arrays
     integer :: isd, jsd
     isd = lbound(Tracer%field, 1); jsd = lbound(Tracer%field, 2)
+    if (Tracer%horz_advect_scheme == ADVECT_MDPPM) then   ! per-tracer field-table entries (ocean_tracer.F90:1006,1051)
+       call check(mom5adv_set_ppm_limiters(handle, int(Tracer%ppm_hlimiter, c_int), int(Tracer%ppm_vlimiter, c_int)), 'ppm limiters')
+    endif
     call check(mom5adv_horz(handle, int(Tracer%horz_advect_scheme, c_int), real(dtime, c_double), &
          c_loc(Tracer%field(isd, jsd, 1, Time%taum1)), c_loc(Tracer%field(isd, jsd, 1, Time%tau)), &
          c_loc(Tracer%tmask_limit), merge(1_c_int, 0_c_int, limit_with_upwind), &

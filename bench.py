@@ -159,13 +159,13 @@ def run_reference(args):
     ms = 1e3 * sorted(times)[len(times) // 2]
     desc["value"] = val
     desc["unit"] = UNIT
-    print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                          ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                          data="synthetic", impl="reference",
-                          config=dict(workload=f"{args.case}: Sweby MDFL advect_tracer_sweby_all, {spec_ntr} tracers; "
-                                               f"CPU sample = {desc['sample']}"),
-                          cpu_baseline=desc,
-                          e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+    emit(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+              ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+              data="synthetic", impl="reference",
+              config=dict(workload=f"{args.case}: Sweby MDFL advect_tracer_sweby_all, {spec_ntr} tracers; "
+                                   f"CPU sample = {desc['sample']}"),
+              cpu_baseline=desc,
+              e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -363,7 +363,9 @@ def run_gpu(args):
         desc["value"], desc["unit"] = val, UNIT
         res["cpu_baseline"] = desc
     if rank == 0:
-        print(json.dumps(res))
+        # flush NOW: with an eagerly initialised NCCL process group the interpreter can leave through the communicator teardown
+        # without draining Python's stdout buffer (seen on the GPU box: exit status 0 and an empty JSON file)
+        emit(res)
     if world > 1:
         dist.barrier()
         if comm:
@@ -413,7 +415,24 @@ def run_e2e(args, adv, spec, b, T, th, out, u, v, w, rho, world, rank, dev, cell
                           + ("j-bands" if os.environ.get("MOM5ADV_BANDED", "1") != "0" and os.environ.get("MOM5ADV_FUSE", "1") != "0" else "tracers") + ")", pcie_gbs=(h2d + d2h) / dt / 1e9)
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line, on the process's original stdout"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line.  Native libraries write there too (NCCL prints its version banner on stdout when
+    # NCCL_DEBUG is set in the environment, whatever NCCL_DEBUG_FILE says): keep a private handle on the real stdout and point
+    # fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("sweep_mode")]
+pytestmark = pytest.mark.gpu
 
 
 def _free_port():
@@ -74,8 +74,9 @@ def _worker(rank, world, port, case, over, px, py, outdir):
     dist.destroy_process_group()
 
 
-def _check(tmp_path, case, over, px, py):
+def _check(tmp_path, case, over, px, py, fuse="1"):
     import torch.multiprocessing as mp
+    os.environ["MOM5ADV_FUSE"] = fuse     # read by mom5adv_init in the spawned workers (they inherit the environment)
     from mom5_b200.synthetic import make_case
     from oracle.oracle import Oracle
     world = px * py
@@ -114,6 +115,15 @@ def _check(tmp_path, case, over, px, py):
     ("global_1deg", dict(ni=1040, nj=80, nk=6, ntr=3), 2, 1), ("global_1deg", dict(ni=1040, nj=80, nk=6, ntr=3), 1, 2)])
 def test_two_gpus(tmp_path, case, over, px, py):
     _check(tmp_path, case, over, px, py)
+
+
+@pytest.mark.parametrize("case,over,px,py", [("mini_tripolar", {}, 2, 1), ("global_1deg", dict(ni=1040, nj=80, nk=6, ntr=3), 1, 2)])
+def test_two_gpus_three_sweep_driver(tmp_path, case, over, px, py):
+    """the second Sweby driver (MOM5ADV_FUSE=0: z, x, y as separate sweeps), incl. its comm-compute overlap branch"""
+    try:
+        _check(tmp_path, case, over, px, py, fuse="0")
+    finally:
+        os.environ.pop("MOM5ADV_FUSE", None)
 
 
 @pytest.mark.parametrize("case,over,px,py", [("mini_tripolar", {}, 2, 2), ("mini_tripolar", {}, 1, 4), ("global_1deg", dict(ntr=3), 2, 2)])

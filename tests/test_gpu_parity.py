@@ -224,6 +224,43 @@ def test_sweby_all_vs_oracle(case, over):
             assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {nm}[{n}]")
 
 
+TINY = [("mini_walls", dict(ni=5, nj=3, nk=1, ntr=1)), ("mini_walls", dict(ni=31, nj=4, nk=2, ntr=2)),
+        ("mini_walls", dict(ni=32, nj=2, nk=3, ntr=3)), ("mini_walls", dict(ni=63, nj=1, nk=4, ntr=4)),
+        ("mini_torus", dict(ni=33, nj=5, nk=2, ntr=5)), ("mini_tripolar", dict(ni=62, nj=9, nk=3, ntr=1)),
+        ("mini_tripolar", dict(ni=130, nj=17, nk=1, ntr=2)), ("mini_torus", dict(ni=4, nj=4, nk=5, ntr=2))]
+
+
+@pytest.mark.parametrize("case,over", TINY)
+def test_sweby_all_tiny_and_ragged_shapes(case, over):
+    """edge shapes: one level, one or two rows, widths around the 31-cell x tile and the 32-lane warp, 5 tracers (groups 3+2),
+    a 4x4 torus whose halo-2 strips wrap onto the whole domain -- device and host-pointer entry points vs the oracle"""
+    from mom5_b200.api import TracerAdvect
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    g = make_case(case, **over)
+    b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    th_ref = [[t.numpy().copy() for t in b.th_tendency]]
+    ref = o.sweby_all([[t.numpy() for t in b.T]], th_ref, g.s.dtime, diag=True)
+    r = _run_sweby_all_dev(b, diag=True)
+    for n in range(len(b.T)):
+        assert_bit_equal(r["th"][n], th_ref[0][n], f"{case} {over} th[{n}]")
+        assert_bit_equal(r["adv"][n], ref["adv"][0][n], f"{case} {over} adv[{n}]")
+        for nm in ("flux_x", "flux_y", "flux_z", "adv_x", "adv_y", "adv_z"):
+            assert_bit_equal(r[nm][n], ref[nm][0][n], f"{case} {over} {nm}[{n}]")
+    r2 = _run_sweby_all_dev(b, diag=False)
+    adv = TracerAdvect(b, ntracers_max=len(b.T))
+    th = [t.numpy().copy() for t in b.th_tendency]
+    out = [np.full_like(t.numpy(), -777.0) for t in b.T]
+    adv.advect_tracer_sweby_all([t.numpy() for t in b.T], th, out, b.uhrho_et.numpy(), b.vhrho_nt.numpy(), b.wrho_bt.numpy(),
+                                b.rho_dzt.numpy(), g.s.dtime)
+    for n in range(len(b.T)):
+        assert_bit_equal(r2["adv"][n], ref["adv"][0][n], f"{case} {over} adv[{n}] without diagnostics")
+        assert_bit_equal(th[n], th_ref[0][n], f"{case} {over} host-pointer th[{n}]")
+        assert_bit_equal(out[n], ref["adv"][0][n], f"{case} {over} host-pointer adv[{n}]")
+    adv.close()
+
+
 @pytest.mark.parametrize("case", ["mini_tripolar", "mini_walls"])
 def test_tiny_and_underflowing_tracers_take_the_exact_division_path(case):
     """Tracer values near the bottom of the binary64 range (a dye patch whose Gaussian tail underflows, a field scaled

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <set>
 #include <cmath>
 
 #include "../../include/mom5adv.h"
@@ -120,6 +121,7 @@ struct mom5adv_ctx {
     cudaEvent_t ev[6];
     bool ev_valid = false;
     int64_t launches = 0;
+    std::set<const void *> smem_ok;    // kernels whose dynamic shared-memory limit has been raised on this handle's device
 };
 
 #ifndef YROWS_MAX
@@ -661,19 +663,13 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
         const unsigned nblk = (unsigned)(g.nk * nxb * (pt.count < 0 ? njc : pt.count));
         if (VAR == VAR_ALL && !DIAG && b.Tnew[0]) {   // time update in the epilogue (mom5adv_sweby_all_step_dev)
             typedef FusedLayout<NT, true> LYU;
-            static bool attr_upd = false;
-            if (!attr_upd) {
+            if (h->smem_ok.insert((const void *)k_sweby_xy<NT, VAR_ALL, false, true>).second)   // once per handle (= per device)
                 CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR_ALL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LYU::BYTES));
-                attr_upd = true;
-            }
             LAUNCH(h, (k_sweby_xy<NT, VAR_ALL, false, true>), nblk, 32 * FWARPS, LYU::BYTES, st, g, b, nxb, nxt);
             return 0;
         }
-        static bool attr_set = false;   // per instantiation
-        if (!attr_set) {
+        if (h->smem_ok.insert((const void *)k_sweby_xy<NT, VAR, DIAG>).second)
             CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedLayout<NT>::BYTES));
-            attr_set = true;
-        }
         LAUNCH(h, (k_sweby_xy<NT, VAR, DIAG>), nblk, 32 * FWARPS, FusedLayout<NT>::BYTES, st, g, b, nxb, nxt);
     }
     return 0;

@@ -100,3 +100,65 @@ def test_xupdate_yupdate_do_not_touch_corners():
         assert (f[:H, :H] == -9).all() and (f[-H:, -H:] == -9).all()          # corners untouched
         assert ((f[H:-H, :H] == 1).all()) == (touched == "ew")
         assert ((f[:H, H:-H] == 1).all()) == (touched == "ns")
+
+
+def _cgrid_pattern():
+    """x / y flux components on a halo-1 global array, FMS pattern on the compute domain (test_mpp_domains.F90:5908-5919)"""
+    g = np.zeros((NZ, NY + 2, NX + 2))
+    for k in range(1, NZ + 1):
+        for j in range(1, NY + 1):
+            for i in range(1, NX + 1):
+                g[k - 1, j, i] = k + i * 1e-3 + j * 1e-6
+    return g
+
+
+def _cgrid_expected_fold_row(g2):
+    """'redundant points must be equal and opposite' (test_mpp_domains.F90:5965): global2(nx/2+1:nx, ny) = -global2(nx/2:1:-1, ny)"""
+    row = g2[:, NY, 1:NX + 1].copy()
+    row[:, NX // 2:] = -row[:, NX // 2 - 1::-1]
+    return row
+
+
+def test_generator_cgrid_ne_filler_matches_fms_kat():
+    """mpp_update_domains(flux_x, flux_y, gridtype=CGRID_NE) on the folded-north domain, as the quicker path uses it
+    (OTA:2640): fold-line rule for the NORTH-position component and the cyclic west / east columns (fill_folded_north_halo's
+    first two statements, :3758-3759) against FMS's own known answer."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from f90interp import FArray
+    from gen_from_reference import Halo
+    dec = Decomposition(NX, NY, 1, 1, cyclic_x=True, tripolar=True)
+    g1, g2 = _cgrid_pattern(), _cgrid_pattern()
+    want_row = _cgrid_expected_fold_row(g2)
+    fx, fy = FArray(data=g1.copy(), lo=[0, 0, 1]), FArray(data=g2.copy(), lo=[0, 0, 1])
+    Halo(dec, 1, NX, 1, NY).cgrid_ne(fx, fy)
+    assert np.array_equal(fy.a[:, NY, 1:NX + 1], want_row)
+    assert np.array_equal(fy.a[:, 1:NY, 1:NX + 1], g2[:, 1:NY, 1:NX + 1])          # nothing else on the compute domain moves
+    assert np.array_equal(fx.a[:, 1:NY + 1, 1:NX + 1], g1[:, 1:NY + 1, 1:NX + 1])
+    assert np.array_equal(fx.a[:, 1:NY + 1, 0], g1[:, 1:NY + 1, NX])                # west halo  = east edge
+    assert np.array_equal(fx.a[:, 1:NY + 1, NX + 1], g1[:, 1:NY + 1, 1])            # east halo  = west edge
+
+
+@pytest.mark.parametrize("layout", [(1, 1), (2, 1), (3, 2), (4, 1), (6, 3)])
+def test_oracle_fold_line_fix_matches_fms_kat(layout):
+    """the oracle's multi-block fold-line fix (orc_fold_fix_flux; the CUDA library's fold_line_fix is checked against it on
+    the GPU) reproduces FMS's known answer for every layout, including mirror images owned by another block"""
+    dec = Decomposition(NX, NY, layout[0], layout[1], cyclic_x=True, tripolar=True)
+    g2 = _cgrid_pattern()
+    want_row = _cgrid_expected_fold_row(g2)
+    fx, fy = [], []
+    for r in range(dec.nranks):
+        i0, i1, j0, j1 = dec.extent(r)
+        f = np.zeros((NZ, j1 - j0 + 3, i1 - i0 + 3))
+        f[:, 1:-1, 1:-1] = g2[:, j0:j1 + 1, i0:i1 + 1]
+        fy.append(f)
+        fx.append(f.copy())
+    ib, ie = (C.c_int * dec.px)(*dec.ibeg), (C.c_int * dec.px)(*dec.iend)
+    jb, je = (C.c_int * dec.py)(*dec.jbeg), (C.c_int * dec.py)(*dec.jend)
+    lay = orc.OrcLayout(NX, NY, dec.px, dec.py, ib, ie, jb, je, 1, 0, 1)
+    orc.lib().orc_fold_fix_flux(C.byref(lay), orc._pp(fx), orc._pp(fy), C.c_int(NZ))
+    for r in range(dec.nranks):
+        i0, i1, j0, j1 = dec.extent(r)
+        want = g2[:, j0:j1 + 1, i0:i1 + 1].copy()
+        if j1 == NY:
+            want[:, -1, :] = want_row[:, i0 - 1:i1]
+        assert np.array_equal(fy[r][:, 1:-1, 1:-1], want), f"layout {layout} rank {r}"

@@ -64,13 +64,14 @@ CONFIGS = [dict(ni_g=40, nj_g=30, px=2, py=2, cyclic_x=True, tripolar=True),
            dict(ni_g=36, nj_g=20, px=2, py=1, cyclic_x=True, tripolar=True)]
 
 
+@pytest.mark.parametrize("halo", [1, 2, 4])    # data-domain fields, MDFL / quicker scratch, MDPPM scratch
 @pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("flags", [XUPDATE, YUPDATE, XUPDATE | YUPDATE])
-def test_exchange_plan_python_equals_library(cfg, flags):
+def test_exchange_plan_python_equals_library(cfg, flags, halo):
     dec = Decomposition(**cfg)
     for rank in range(dec.nranks):
-        sends, recvs = dec.exchange_plan(rank, flags, halo=2)
-        ls, lr = _lib_plan(dec, rank, flags)
+        sends, recvs = dec.exchange_plan(rank, flags, halo=halo)
+        ls, lr = _lib_plan(dec, rank, flags, halo)
         assert [(m.peer, m.i0, m.i1, m.j0, m.j1, int(m.flip)) for m in sends] == ls
         assert [(m.peer, m.i0, m.i1, m.j0, m.j1, int(m.flip)) for m in recvs] == lr
 
@@ -98,11 +99,12 @@ def _apply_plans(dec, fields, flags, halo=2):
             fields[r][:, m.j0 - 1 + halo:m.j1 + halo, m.i0 - 1 + halo:m.i1 + halo] = blk
 
 
+@pytest.mark.parametrize("halo", [1, 2, 4])
 @pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("flags", [XUPDATE, YUPDATE, XUPDATE | YUPDATE])
-def test_plan_execution_equals_oracle_update(cfg, flags):
+def test_plan_execution_equals_oracle_update(cfg, flags, halo):
     dec = Decomposition(**cfg)
-    nk, halo = 3, 2
+    nk = 3
     rng = np.random.default_rng(5)
     a, b = [], []
     for r in range(dec.nranks):

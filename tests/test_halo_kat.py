@@ -47,9 +47,18 @@ def expected_global(kind):
 KINDS = {"Simple": dict(), "Cyclic": dict(cyclic_x=True, cyclic_y=True), "Folded-north": dict(cyclic_x=True, tripolar=True)}
 
 
+@pytest.fixture(params=[2, 4, 1])
+def halo_width(request):
+    """the KAT at the three halo widths of the path: 2 (MDFL / quicker scratch), 4 (MDPPM scratch), 1 (data-domain fields)"""
+    global H
+    old, H = H, request.param
+    yield request.param
+    H = old
+
+
 @pytest.mark.parametrize("kind", list(KINDS))
 @pytest.mark.parametrize("layout", [(1, 1), (2, 2), (3, 2), (4, 1), (1, 3)])
-def test_oracle_update_matches_fms_kat(kind, layout):
+def test_oracle_update_matches_fms_kat(kind, layout, halo_width):
     dec = Decomposition(NX, NY, layout[0], layout[1], **KINDS[kind])
     exp = expected_global(kind)
     fields = []
@@ -69,7 +78,7 @@ def test_oracle_update_matches_fms_kat(kind, layout):
 
 
 @pytest.mark.parametrize("kind", list(KINDS))
-def test_golden_generator_filler_matches_fms_kat(kind):
+def test_golden_generator_filler_matches_fms_kat(kind, halo_width):
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     from f90interp import FArray
     from gen_from_reference import Halo

@@ -179,6 +179,11 @@ int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_scheme, dou
                          const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
                          const double *rho_dzt_tau, const double *rho_dzt_taup1, const double *advect_tendency,
                          double *adv_diss, double *t2_tendency, void *stream);
+int mom5adv_adv_diss(mom5adv_handle h, int horz_scheme, int vert_scheme, double dtime, double conversion,
+                     const double *T_tau, const double *tmask_limit, int limit_with_upwind,
+                     const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
+                     const double *rho_dzt_tau, const double *rho_dzt_taup1, const double *advect_tendency,
+                     double *adv_diss, double *t2_tendency);   /* host-pointer twin, synchronous */
 int mom5adv_flux_int_z_dev(mom5adv_handle h, const double *flux3d, double *out2d, void *stream);
 
 /* ---- metrics on device arrays ---------------------------------------------------------------------------

@@ -44,6 +44,7 @@ SYMBOLS = {
     "mom5adv_continuity_dev": (C.c_int, [_v, dp, dp, dp, dp, dp, dp, _v]),
     "mom5adv_set_ppm_limiters": (C.c_int, [_v, C.c_int, C.c_int]),
     "mom5adv_adv_diss_dev": (C.c_int, [_v, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, _v]),
+    "mom5adv_adv_diss": (C.c_int, [_v, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]),
     "mom5adv_flux_int_z_dev": (C.c_int, [_v, dp, dp, _v]),
     "mom5adv_chksum_dev": (C.c_int, [_v, dp, C.c_int, C.POINTER(C.c_int64), _v]),
     "mom5adv_total_tracer_dev": (C.c_int, [_v, dp, dp, dp, _v]),

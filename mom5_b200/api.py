@@ -191,10 +191,13 @@ class TracerAdvect:
     # ---- diagnostics producers: compute_adv_diss (OTA:7547-7712), z-integrated fluxes (OTA:4317-4326) ----
     def adv_diss(self, horz_scheme: int, vert_scheme: int, T_tau, advect_tendency, uhrho_et, vhrho_nt, wrho_bt, rho_dzt_tau,
                  rho_dzt_taup1, dtime: float, adv_diss_out, conversion: float = 1.0, tmask_limit=None, t2_tendency=None):
-        check(self.L.mom5adv_adv_diss_dev(self.handle, int(horz_scheme), int(vert_scheme), float(dtime), float(conversion),
-                                          _ptr(T_tau), _ptr(tmask_limit), int(self.limit_with_upwind), _ptr(uhrho_et), _ptr(vhrho_nt),
-                                          _ptr(wrho_bt), _ptr(rho_dzt_tau), _ptr(rho_dzt_taup1), _ptr(advect_tendency),
-                                          _ptr(adv_diss_out), _ptr(t2_tendency), _cur_stream()), "adv_diss_dev")
+        args = [self.handle, int(horz_scheme), int(vert_scheme), float(dtime), float(conversion), _ptr(T_tau), _ptr(tmask_limit),
+                int(self.limit_with_upwind), _ptr(uhrho_et), _ptr(vhrho_nt), _ptr(wrho_bt), _ptr(rho_dzt_tau), _ptr(rho_dzt_taup1),
+                _ptr(advect_tendency), _ptr(adv_diss_out), _ptr(t2_tendency)]
+        if _on_device(T_tau):
+            check(self.L.mom5adv_adv_diss_dev(*args, _cur_stream()), "adv_diss_dev")
+        else:
+            check(self.L.mom5adv_adv_diss(*args), "adv_diss")
 
     def flux_int_z(self, flux3d, out2d):
         check(self.L.mom5adv_flux_int_z_dev(self.handle, _ptr(flux3d), _ptr(out2d), _cur_stream()), "flux_int_z_dev")

@@ -1449,6 +1449,35 @@ extern "C" int mom5adv_adv_diss_dev(mom5adv_handle h, int horz_scheme, int vert_
     return 0;
 }
 
+// host-pointer twin (what the Fortran shim binds at OTA:2221-2223): H2D of the operands, the device path, D2H of the results
+extern "C" int mom5adv_adv_diss(mom5adv_handle h, int horz_scheme, int vert_scheme, double dtime, double conversion,
+                                const double *T_tau, const double *tlimit, int limit_with_upwind, const double *u, const double *v,
+                                const double *w, const double *rho_tau, const double *rho_taup1, const double *advect_tendency,
+                                double *adv_diss, double *t2_tendency)
+{
+    if (!h || !T_tau || !u || !v || !w || !rho_tau || !rho_taup1 || !advect_tendency || !adv_diss) {
+        set_error("mom5adv_adv_diss: null argument");
+        return MOM5ADV_EINVAL;
+    }
+    cudaStream_t st = h->stream;
+    const size_t N = n3(h);
+    int rc;
+    size_t slot = 6;   // slots 0,1 are the flux work arrays of the dispatchers, 2..5 the work arrays of mom5adv_adv_diss_dev
+    double *dT, *dtl = 0, *du, *dv, *dw, *dr0, *dr1, *dadv, *ddiss, *dt2 = 0;
+    if ((rc = mirror(h, slot++, &dT)) || (rc = mirror(h, slot++, &du)) || (rc = mirror(h, slot++, &dv)) || (rc = mirror(h, slot++, &dr0)) ||
+        (rc = mirror(h, slot++, &dr1)) || (rc = mirror(h, slot++, &dadv)) || (rc = mirror(h, slot++, &ddiss)) || (rc = mirror_w(h, &dw))) return rc;
+    H2D(dT, T_tau, N); H2D(du, u, N); H2D(dv, v, N); H2D(dr0, rho_tau, N); H2D(dr1, rho_taup1, N); H2D(dadv, advect_tendency, N);
+    H2D(dw, w, (size_t)h->g.slab * (h->g.nk + 1));
+    if (tlimit) { if ((rc = mirror(h, slot++, &dtl))) return rc; H2D(dtl, tlimit, N); }
+    if (t2_tendency && (rc = mirror(h, slot++, &dt2))) return rc;
+    if ((rc = mom5adv_adv_diss_dev(h, horz_scheme, vert_scheme, dtime, conversion, dT, dtl, limit_with_upwind, du, dv, dw, dr0, dr1, dadv,
+                                   ddiss, dt2, st))) return rc;
+    D2H(adv_diss, ddiss, N);
+    if (t2_tendency) D2H(t2_tendency, dt2, N);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int mom5adv_set_ppm_limiters(mom5adv_handle h, int ppm_hlimiter, int ppm_vlimiter)
 {
     if (!h) { set_error("mom5adv_set_ppm_limiters: null handle"); return MOM5ADV_EINVAL; }

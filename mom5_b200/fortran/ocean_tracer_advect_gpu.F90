@@ -78,6 +78,15 @@ module ocean_tracer_advect_gpu_mod
        type(c_ptr), value :: Tm1, Tt, tlimit, u, v, w, rho, th, wrk1, fx, fy, fz
        integer(c_int) :: rc
      end function
+     function mom5adv_adv_diss(handle, horz_scheme, vert_scheme, dtime, conversion, T_tau, tlimit, limit_with_upwind, &
+          u, v, w, rho_tau, rho_taup1, advect_tendency, adv_diss, t2_tendency) bind(C, name='mom5adv_adv_diss') result(rc)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value    :: handle
+       integer(c_int), value :: horz_scheme, vert_scheme, limit_with_upwind
+       real(c_double), value :: dtime, conversion
+       type(c_ptr), value    :: T_tau, tlimit, u, v, w, rho_tau, rho_taup1, advect_tendency, adv_diss, t2_tendency
+       integer(c_int)        :: rc
+     end function mom5adv_adv_diss
      function mom5adv_set_ppm_limiters(handle, ppm_hlimiter, ppm_vlimiter) bind(C, name='mom5adv_set_ppm_limiters') result(rc)
        import :: c_ptr, c_int
        type(c_ptr), value    :: handle
@@ -201,6 +210,29 @@ contains
          c_loc(Tracer%tmask_limit), c_loc(Adv_vel%wrho_bt), c_loc(Tracer%th_tendency), c_loc(Tracer%wrk1), &
          c_loc(flux_z)), 'vert_advect_tracer')
   end subroutine gpu_vert_advect_tracer
+
+  ! replaces compute_adv_diss (OTA:7547-7712) up to its diagnose_3d calls: wrk4 = adv_diss, wrk1 = tendency of the squared tracer
+  subroutine gpu_compute_adv_diss(Time, Adv_vel, Thickness, Tracer, dtime, limit_with_upwind, advect_tendency, wrk1, wrk4)
+    type(ocean_time_type),        intent(in)            :: Time
+    type(ocean_adv_vel_type),     intent(in),    target :: Adv_vel
+    type(ocean_thickness_type),   intent(in),    target :: Thickness
+    type(ocean_prog_tracer_type), intent(inout), target :: Tracer
+    real,                         intent(in)            :: dtime
+    logical,                      intent(in)            :: limit_with_upwind
+    real, dimension(:,:,:),       intent(in),    target :: advect_tendency
+    real, dimension(:,:,:),       intent(inout), target :: wrk1, wrk4
+    integer :: isd, jsd
+    isd = lbound(Tracer%field, 1); jsd = lbound(Tracer%field, 2)
+    if (Tracer%horz_advect_scheme == ADVECT_MDPPM) then
+       call check(mom5adv_set_ppm_limiters(handle, int(Tracer%ppm_hlimiter, c_int), int(Tracer%ppm_vlimiter, c_int)), 'ppm limiters')
+    endif
+    call check(mom5adv_adv_diss(handle, int(Tracer%horz_advect_scheme, c_int), int(Tracer%vert_advect_scheme, c_int), &
+         real(dtime, c_double), real(Tracer%conversion, c_double), c_loc(Tracer%field(isd, jsd, 1, Time%tau)), &
+         c_loc(Tracer%tmask_limit), merge(1_c_int, 0_c_int, limit_with_upwind), &
+         c_loc(Adv_vel%uhrho_et), c_loc(Adv_vel%vhrho_nt), c_loc(Adv_vel%wrho_bt), &
+         c_loc(Thickness%rho_dzt(isd, jsd, 1, Time%tau)), c_loc(Thickness%rho_dzt(isd, jsd, 1, Time%taup1)), &
+         c_loc(advect_tendency), c_loc(wrk4), c_loc(wrk1)), 'compute_adv_diss')
+  end subroutine gpu_compute_adv_diss
 
   subroutine gpu_tracer_advect_end()
     integer(c_int) :: rc

@@ -386,6 +386,26 @@ def test_adv_diss_vs_reference_golden(name, tag, sweep_mode):
     adv.close()
 
 
+@pytest.mark.parametrize("tag", ["quicker_lim", "mdfl_sweby", "mdppm_sh"])
+def test_adv_diss_host_pointer_entry(tag):
+    """the host-pointer twin the Fortran shim binds at vert_advect_tracer's tail (OTA:2221-2223)"""
+    from mom5_b200.api import SCHEME_IDS, TracerAdvect
+    b, gold, _ = load_golden("g_tripolar")
+    n = int(gold[f"{tag}.tracer"]) - 1
+    scheme = SCHEME_IDS[tag.replace("_lim", "").split("_sh")[0]]
+    adv = TracerAdvect(b, ntracers_max=1, limit_with_upwind=(tag == "quicker_lim"))
+    if tag.startswith("mdppm"):
+        adv.set_ppm_limiters(3)
+    rho = b.rho_dzt.numpy()
+    diss, t2 = np.full_like(rho, -777.0), np.full_like(rho, -777.0)
+    adv.adv_diss(scheme, scheme, b.T_tau[n].numpy(), gold[f"{tag}.advect_tendency"], b.uhrho_et.numpy(), b.vhrho_nt.numpy(),
+                 b.wrho_bt.numpy(), rho, (b.rho_dzt * 1.01).numpy(), b.spec.dtime, diss, conversion=float(gold[f"{tag}.conversion"]),
+                 tmask_limit=b.tmask_limit[n].numpy(), t2_tendency=t2)
+    assert_bit_equal(t2, gold[f"{tag}.adv_diss.t2_tendency"], "advection of the squared tracer")
+    assert_bit_equal(diss, gold[f"{tag}.adv_diss"], "adv_diss")
+    adv.close()
+
+
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_z_integrated_fluxes_vs_reference_golden(name, sweep_mode):
     """*_xflux_adv_int_z / *_yflux_adv_int_z (OTA:4317-4326, 4449-4458) from the device fluxes of sweby_all"""

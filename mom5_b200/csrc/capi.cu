@@ -526,6 +526,14 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     g.tpitch = ((g.ni + TOFF + 3) + 15) / 16 * 16; g.tslab = (long long)g.tpitch * (g.nj + 4);
     g.mpitch = g.tpitch; g.mslab = g.tslab;
     g.p4 = g.ni + 8; g.s4 = (long long)g.p4 * (g.nj + 8);
+    {   // a halo strip must come from ONE neighbour (FMS refuses halos wider than the compute domain as well)
+        const bool src_x = h->cyclic_x || h->px > 1, src_y = h->cyclic_y || h->py > 1 || h->tripolar;
+        if ((src_x && g.ni < 2) || (src_y && g.nj < 2)) {
+            set_error("mom5adv_init: local block %dx%d is narrower than the width-2 halo it has to fill", g.ni, g.nj);
+            delete h;
+            return MOM5ADV_EUNSUP;
+        }
+    }
     if ((unsigned long long)g.tslab * (unsigned long long)g.nk >= (1ull << 32) || (unsigned long long)g.slab * (unsigned long long)(g.nk + 2) >= (1ull << 32)) {
         set_error("mom5adv_init: local block too large (the kernels index with 32-bit element offsets: < 2^32 elements per array)");
         delete h;
@@ -1249,6 +1257,13 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
             return MOM5ADV_EINVAL;
         }
         int rc;
+        {
+            const bool src_x = h->cyclic_x || h->px > 1, src_y = h->cyclic_y || h->py > 1 || h->tripolar;
+            if ((src_x && g.ni < 4) || (src_y && g.nj < 4)) {
+                set_error("mom5adv_horz_dev: mdppm needs a local block of at least 4x4 cells for its width-4 halo (have %dx%d)", g.ni, g.nj);
+                return MOM5ADV_EUNSUP;
+            }
+        }
         const size_t n4 = (size_t)g.s4 * g.nk;
         if (!h->pp_tr) {
             CUDA_TRY(cudaMalloc(&h->pp_tr, n4 * sizeof(double)));

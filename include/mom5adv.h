@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MOM5ADV_VERSION 100
+#define MOM5ADV_VERSION 200
 
 /* error codes */
 #define MOM5ADV_OK 0
@@ -80,6 +80,14 @@ int mom5adv_comm_unique_id(char id_out[128]);
 int mom5adv_comm_create(const char id[128], int rank, int nranks, mom5adv_comm *out);
 int mom5adv_comm_from_nccl(void *nccl_comm, int rank, int nranks, mom5adv_comm *out);
 int mom5adv_comm_destroy(mom5adv_comm c);
+
+/* ---- device selection -----------------------------------------------------------------------------------
+ * One rank drives one GPU.  A multi-rank host (the MPI Fortran model) calls mom5adv_set_device with its NODE-LOCAL rank
+ * before mom5adv_comm_create / mom5adv_init: the rank is bound to device (rank mod device count), as FMS binds ranks to
+ * cores (src/shared/mpp/affinity.c:67).  Without it every rank would land on device 0 and ncclCommInitRank would refuse
+ * the duplicate GPU.  A host that already selected a device (torch.cuda.set_device) does not need to call it.        */
+int mom5adv_device_count(int *count);
+int mom5adv_set_device(int node_local_rank);
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
 int mom5adv_init(const mom5adv_grid *grid, int ntracers_max, mom5adv_comm comm_or_null, mom5adv_handle *out);

@@ -27,6 +27,8 @@ _v = C.c_void_p
 SYMBOLS = {
     "mom5adv_last_error": (C.c_char_p, []),
     "mom5adv_version": (C.c_int, []),
+    "mom5adv_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mom5adv_set_device": (C.c_int, [C.c_int]),
     "mom5adv_comm_unique_id": (C.c_int, [C.c_char_p]),
     "mom5adv_comm_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_v)]),
     "mom5adv_comm_from_nccl": (C.c_int, [_v, C.c_int, C.c_int, C.POINTER(_v)]),

@@ -8,7 +8,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <set>
+#include <tuple>
 #include <cmath>
 
 #include "../../include/mom5adv.h"
@@ -17,6 +19,8 @@
 #include "mom5adv_internal.cuh"
 #include "sweby_kernels.cuh"
 #include "sweby_fused.cuh"
+#include "sweby_z_tma.cuh"
+#include "sweby_fused_tma.cuh"
 #include "sweby_test_kernels.cuh"
 #include "mdppm_kernels.cuh"
 
@@ -80,6 +84,38 @@ static NcclApi *nccl_api()
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// tensor maps (TMA descriptors).  The encoder lives in the driver library; it is fetched through the runtime so that the
+// library carries no link-time dependency on libcuda.
+// ------------------------------------------------------------------------------------------------
+struct TmapKey {
+    const void *base;
+    unsigned long long n0, n1, n2;
+    unsigned b0, b1, b2;
+    bool operator<(const TmapKey &o) const
+    {
+        return std::tie(base, n0, n1, n2, b0, b1, b2) < std::tie(o.base, o.n0, o.n1, o.n2, o.b0, o.b1, o.b2);
+    }
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
 struct mom5adv_ctx {
@@ -98,6 +134,7 @@ struct mom5adv_ctx {
     double *st_ms = 0;                 // mass_mdfl of advect_tracer_mdfl_sweby_test (h2 scratch, allocated on first use)
     double *pp_fz = 0;                 // MDPPM: flux_z work array when the caller does not want it
     double *pp_tr = 0, *pp_m4 = 0, *pp_da = 0;   // MDPPM: tracer_mdppm, tmask_mdppm, slope scratch (h4, allocated on first use)
+    bool pp_ready = false;             // tmask_mdppm filled and halo-updated
     HaloPlan plan4[4];                 // halo-4 updates (Dom_mdppm, OTA:1706), indexed by flags
     int ppm_hlimiter = 1, ppm_vlimiter = 1;      // Tracer%ppm_hlimiter / ppm_vlimiter defaults (ocean_types.F90:1018-1019)
     // halo machinery
@@ -111,17 +148,22 @@ struct mom5adv_ctx {
     cudaStream_t stream = 0;           // library-owned stream for the host-pointer entry points
     cudaStream_t s_up = 0, s_down = 0; // copy streams of the pipelined host-pointer path
     cudaStream_t s_comm = 0;           // halo exchange stream (overlapped with interior tiles)
-    cudaEvent_t ev_sync[4];
+    cudaEvent_t ev_sync[4] = {};
     int overlap = 1;                   // MOM5ADV_OVERLAP=0 disables the comm/compute overlap
     int y_rows = 32;
     int fuse = 1;                      // MOM5ADV_FUSE=0: three separate sweeps instead of z + fused x/y
+    int tma = 1;                       // MOM5ADV_TMA=0: per-thread LDGSTS staging instead of TMA bulk copies (also used for unaligned bases)
     int f_rows = 64;
     std::vector<cudaEvent_t> ev_up, ev_done;
     int banded = 1;                    // MOM5ADV_BANDED=0: host-pointer sweby_all pipelines over tracers instead of j-bands
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[6] = {};
     bool ev_valid = false;
     int64_t launches = 0;
     std::set<const void *> smem_ok;    // kernels whose dynamic shared-memory limit has been raised on this handle's device
+    double *met_ring = 0, *met_y = 0;  // packed 2-D metrics for the TMA-staged fused pass: (dyte, datr) and (dxtn, dytn) planes
+    unsigned *zbits = 0;               // per-column mask bit strings for the z sweep (k_build_zbits), nzw words per column
+    int nzw = 0;
+    std::map<TmapKey, CUtensorMap> tmaps;   // tensor maps by (base pointer, extents, box): encoded once per caller array
 };
 
 #ifndef YROWS_MAX
@@ -138,7 +180,29 @@ struct mom5adv_ctx {
     } while (0)
 
 static size_t n3(const mom5adv_ctx *h) { return (size_t)h->g.slab * h->g.nk; }
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+#define NIB_PAD 16   // the mask-nibble arrays are allocated NIB_PAD bytes long so that a staged row's 16-byte span never has to be clipped
 static size_t nh2(const mom5adv_ctx *h) { return (size_t)h->g.tslab * h->g.nk; }
+
+// ------------------------------------------------------------------------------------------------
+// device selection (one rank per GPU: the Fortran shim calls this with its node-local rank before mom5adv_init)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mom5adv_device_count(int *count)
+{
+    if (!count) { set_error("mom5adv_device_count: null argument"); return MOM5ADV_EINVAL; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { *count = 0; set_error("mom5adv_device_count: no CUDA device"); return MOM5ADV_ENOGPU; }
+    *count = n;
+    return 0;
+}
+extern "C" int mom5adv_set_device(int node_local_rank)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { set_error("mom5adv_set_device: no CUDA device"); return MOM5ADV_ENOGPU; }
+    if (node_local_rank < 0) { set_error("mom5adv_set_device: negative rank"); return MOM5ADV_EINVAL; }
+    CUDA_TRY(cudaSetDevice(node_local_rank % n));
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // layout helpers (mpp_compute_extent, MPPI/mpp_domains_define.inc:187-273)
@@ -480,6 +544,7 @@ static int upload(T **dst, const T *src, size_t n)
 
 static int quicker_setup(mom5adv_ctx *h, const mom5adv_grid *G, cudaStream_t st);
 static int mirror(mom5adv_ctx *h, size_t idx, double **out);
+static int init_body(mom5adv_ctx *h, const mom5adv_grid *G, int ntracers_max, mom5adv_comm comm);
 
 extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_comm comm, mom5adv_handle *out)
 {
@@ -490,6 +555,15 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     if (G->tripolar && G->cyclic_y) { set_error("mom5adv_init: tripolar and cyclic_y are exclusive"); return MOM5ADV_EINVAL; }
     if (G->tripolar && (G->ni_global % 2)) { set_error("mom5adv_init: tripolar fold needs an even ni_global"); return MOM5ADV_EINVAL; }
     mom5adv_ctx *h = new mom5adv_ctx();
+    // every failure below goes through ONE cleanup: mom5adv_finalize copes with a partially built context
+    const int rc = init_body(h, G, ntracers_max, comm);
+    if (rc) { mom5adv_finalize(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+static int init_body(mom5adv_ctx *h, const mom5adv_grid *G, int ntracers_max, mom5adv_comm comm)
+{
     h->ntr_max = ntracers_max;
     h->ni_g = G->ni_global; h->nj_g = G->nj_global; h->px = G->layout_x; h->py = G->layout_y;
     h->cyclic_x = G->cyclic_x; h->cyclic_y = G->cyclic_y; h->tripolar = G->tripolar;
@@ -502,20 +576,18 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     };
     int rc = G->x_extent ? from_extent(G->x_extent, h->px, h->ni_g, h->ibeg, h->iend) : compute_extent(1, h->ni_g, h->px, h->ibeg, h->iend);
     rc |= G->y_extent ? from_extent(G->y_extent, h->py, h->nj_g, h->jbeg, h->jend) : compute_extent(1, h->nj_g, h->py, h->jbeg, h->jend);
-    if (rc) { set_error("mom5adv_init: invalid domain extents"); delete h; return MOM5ADV_EINVAL; }
+    if (rc) { set_error("mom5adv_init: invalid domain extents"); return MOM5ADV_EINVAL; }
     h->ix = find_div(h->ibeg, h->iend, G->isc);
     h->iy = find_div(h->jbeg, h->jend, G->jsc);
     if (h->ix < 0 || h->iy < 0 || h->ibeg[h->ix] != G->isc || h->iend[h->ix] != G->iec || h->jbeg[h->iy] != G->jsc ||
         h->jend[h->iy] != G->jec) {
         set_error("mom5adv_init: compute domain (%d:%d,%d:%d) does not match layout %dx%d", G->isc, G->iec, G->jsc, G->jec, h->px, h->py);
-        delete h;
         return MOM5ADV_EINVAL;
     }
     h->rank = h->ix + h->px * h->iy;
     if (h->px * h->py > 1) {
         if (!comm || comm->nranks != h->px * h->py || comm->rank != h->rank) {
             set_error("mom5adv_init: layout %dx%d needs a communicator with %d ranks and rank == ix + px*iy", h->px, h->py, h->px * h->py);
-            delete h;
             return MOM5ADV_EINVAL;
         }
         h->comm = comm;
@@ -530,22 +602,26 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
         const bool src_x = h->cyclic_x || h->px > 1, src_y = h->cyclic_y || h->py > 1 || h->tripolar;
         if ((src_x && g.ni < 2) || (src_y && g.nj < 2)) {
             set_error("mom5adv_init: local block %dx%d is narrower than the width-2 halo it has to fill", g.ni, g.nj);
-            delete h;
             return MOM5ADV_EUNSUP;
         }
     }
     if ((unsigned long long)g.tslab * (unsigned long long)g.nk >= (1ull << 32) || (unsigned long long)g.slab * (unsigned long long)(g.nk + 2) >= (1ull << 32)) {
         set_error("mom5adv_init: local block too large (the kernels index with 32-bit element offsets: < 2^32 elements per array)");
-        delete h;
         return MOM5ADV_EUNSUP;
     }
     const size_t n2 = (size_t)g.slab;
     if (upload(&h->dat, G->dat, n2) || upload(&h->datr, G->datr, n2) || upload(&h->dxte, G->dxte, n2) ||
         upload(&h->dyte, G->dyte, n2) || upload(&h->dxtn, G->dxtn, n2) || upload(&h->dytn, G->dytn, n2) ||
-        upload(&h->tmask, G->tmask, n3(h))) { delete h; return MOM5ADV_ECUDA; }
+        upload(&h->tmask, G->tmask, n3(h))) return MOM5ADV_ECUDA;
+    CUDA_TRY(cudaMalloc(&h->met_ring, 2 * n2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->met_y, 2 * n2 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->met_ring, h->dyte, n2 * sizeof(double), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(h->met_ring + n2, h->datr, n2 * sizeof(double), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(h->met_y, h->dxtn, n2 * sizeof(double), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(h->met_y + n2, h->dytn, n2 * sizeof(double), cudaMemcpyDeviceToDevice));
     CUDA_TRY(cudaMalloc(&h->mask, (size_t)g.mslab * g.nk));
     CUDA_TRY(cudaMemset(h->mask, 0, (size_t)g.mslab * g.nk));
-    h->tmA.resize(ntracers_max); h->tmB.resize(ntracers_max);
+    h->tmA.assign(ntracers_max, nullptr); h->tmB.assign(ntracers_max, nullptr);
     for (int n = 0; n < ntracers_max; n++) {
         CUDA_TRY(cudaMalloc(&h->tmA[n], nh2(h) * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->tmB[n], nh2(h) * sizeof(double)));
@@ -554,13 +630,19 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    {   // the halo stream outranks the compute stream: its pack / NCCL / unpack kernels are scheduled ahead of the (tens of
+        // thousands of) interior blocks already queued, so the exchange starts at once instead of behind them
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, prio_hi));
+    }
     for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sync[e], cudaEventDisableTiming));
     if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
     if (const char *fu = getenv("MOM5ADV_FUSE")) h->fuse = atoi(fu);
+    if (const char *tm = getenv("MOM5ADV_TMA")) h->tma = atoi(tm);
     if (const char *bd = getenv("MOM5ADV_BANDED")) h->banded = atoi(bd);
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
-    h->ev_up.resize(ntracers_max); h->ev_done.resize(ntracers_max);
+    h->ev_up.assign(ntracers_max, nullptr); h->ev_done.assign(ntracers_max, nullptr);
     for (int n = 0; n < ntracers_max; n++) {
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_up[n], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[n], cudaEventDisableTiming));
@@ -579,16 +661,21 @@ extern "C" int mom5adv_init(const mom5adv_grid *G, int ntracers_max, mom5adv_com
     if ((rc = halo_update(h, f0, 1, 3, st))) { return rc; }
     dim3 gm((g.ni + 4 + 127) / 128, g.nj + 4, g.nk);
     LAUNCH(h, k_h2_to_mask, gm, 128, 0, st, g, h->tmA[0], h->mask);
-    CUDA_TRY(cudaMalloc(&h->nibz, n3(h)));
-    CUDA_TRY(cudaMalloc(&h->nibx, n3(h)));
-    CUDA_TRY(cudaMalloc(&h->niby, n3(h)));
+    CUDA_TRY(cudaMalloc(&h->nibz, n3(h) + 2 * NIB_PAD));
+    CUDA_TRY(cudaMalloc(&h->nibx, n3(h) + 2 * NIB_PAD));
+    CUDA_TRY(cudaMalloc(&h->niby, n3(h) + 2 * NIB_PAD));
+    CUDA_TRY(cudaMemsetAsync(h->nibz + n3(h), 0, 2 * NIB_PAD, st));
+    CUDA_TRY(cudaMemsetAsync(h->nibx + n3(h), 0, 2 * NIB_PAD, st));
+    CUDA_TRY(cudaMemsetAsync(h->niby + n3(h), 0, 2 * NIB_PAD, st));
     LAUNCH(h, k_build_nibbles, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, h->mask, h->nibz, h->nibx, h->niby);
+    h->nzw = (g.nk + 3 + 31) / 32;
+    CUDA_TRY(cudaMalloc(&h->zbits, (size_t)h->nzw * g.slab * sizeof(unsigned)));
+    LAUNCH(h, k_build_zbits, dim3((g.ni + 2 + 127) / 128, g.nj + 2), 128, 0, st, g, h->mask, h->zbits, h->nzw);
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaMemset(h->tmA[0], 0, nh2(h) * sizeof(double)));
     if ((rc = quicker_setup(h, G, st))) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
-    *out = h;
     return 0;
 }
 
@@ -596,22 +683,22 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
 {
     if (!h) return 0;
     cudaDeviceSynchronize();
-    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms, h->pp_tr, h->pp_m4, h->pp_da, h->pp_fz})
+    cudaGetLastError();   // a failed init leaves a sticky-free error behind; the frees below must not trip over it
+    for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms, h->pp_tr, h->pp_m4, h->pp_da, h->pp_fz,
+                      h->met_ring, h->met_y})
         if (p) cudaFree(p);
     for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
         if (p) cudaFree(p);
-    for (double *p : h->tmA) cudaFree(p);
-    for (double *p : h->tmB) cudaFree(p);
-    for (double *p : h->hm) cudaFree(p);
+    if (h->zbits) cudaFree(h->zbits);
+    for (double *p : h->tmA) if (p) cudaFree(p);
+    for (double *p : h->tmB) if (p) cudaFree(p);
+    for (double *p : h->hm) if (p) cudaFree(p);
     free_quickw(h->qw);
-    for (int e = 0; e < 6; e++) cudaEventDestroy(h->ev[e]);
-    cudaStreamDestroy(h->stream);
-    cudaStreamDestroy(h->s_up);
-    cudaStreamDestroy(h->s_comm);
-    for (int e = 0; e < 4; e++) cudaEventDestroy(h->ev_sync[e]);
-    cudaStreamDestroy(h->s_down);
-    for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    for (int e = 0; e < 6; e++) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
+    for (cudaStream_t s : {h->stream, h->s_up, h->s_comm, h->s_down}) if (s) cudaStreamDestroy(s);
+    for (int e = 0; e < 4; e++) if (h->ev_sync[e]) cudaEventDestroy(h->ev_sync[e]);
+    for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -636,6 +723,81 @@ struct Part {
 };
 enum { PH_Z = 0, PH_X = 1, PH_Y = 2, PH_XY = 3 };
 
+// 3-D FP64 tensor map over an array dimensioned (n0, n1, n2) Fortran-style (n0 contiguous), box b0 x b1 x b2
+static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsigned long long n1, unsigned long long n2, unsigned b0,
+                 unsigned b1, unsigned b2, CUtensorMap *out)
+{
+    const TmapKey key{base, n0, n1, n2, b0, b1, b2};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) { *out = it->second; return 0; }
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return MOM5ADV_ECUDA; }
+    const cuuint64_t dims[3] = {n0, n1, n2};
+    const cuuint64_t strides[2] = {n0 * sizeof(double), n0 * n1 * sizeof(double)};
+    const cuuint32_t box[3] = {b0, b1, b2}, estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %llux%llux%llu array, box %ux%ux%u", (int)r, n0, n1, n2, b0, b1, b2); return MOM5ADV_ECUDA; }
+    if (h->tmaps.size() > 4096) h->tmaps.clear();   // callers that hand in fresh allocations every step must not grow the cache forever
+    h->tmaps[key] = m;
+    *out = m;
+    return 0;
+}
+
+// TMA staging needs 16-byte aligned bases and row strides that are multiples of 16 bytes (an even ni+2)
+static bool tma_ok(const mom5adv_ctx *h) { return h->tma && (h->g.nxd % 2 == 0) && tma_encoder() != nullptr; }
+
+template <int NT, int VAR, bool DIAG>
+static int launch_z_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, dim3 grid, cudaStream_t st)
+{
+    const Geom &g = h->g;
+    ZMaps<NT> m;
+    int rc;
+    for (int n = 0; n < NT; n++)
+        if ((rc = tmap3(h, b.T[n], g.nxd, g.nyd, g.nk, ZBX, 1, ZT_KC, &m.T[n]))) return rc;
+    if ((rc = tmap3(h, b.w, g.nxd, g.nyd, g.nk + 1, ZBX, 1, ZT_KC, &m.w)) || (rc = tmap3(h, b.rho, g.nxd, g.nyd, g.nk, ZBX, 1, ZT_KC, &m.rho))) return rc;
+    if (h->smem_ok.insert((const void *)k_sweby_z_tma<NT, VAR, DIAG>).second)
+        CUDA_TRY(cudaFuncSetAttribute(k_sweby_z_tma<NT, VAR, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZTLayout<NT>::BYTES));
+    LAUNCH(h, (k_sweby_z_tma<NT, VAR, DIAG>), grid, ZBX, ZTLayout<NT>::BYTES, st, g, b, m, h->zbits, h->nzw);
+    return 0;
+}
+
+template <int NT, int VAR, bool DIAG, bool UPD>
+static int launch_xy_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, unsigned nblk, int nxb, int nxt, cudaStream_t st)
+{
+    const Geom &g = h->g;
+    typedef FusedTmaLayout<NT, UPD> LY;
+    FusedMaps<NT, UPD> m;
+    memset(&m, 0, sizeof m);
+    int rc;
+    const unsigned long long nx = g.nxd, ny = g.nyd, nk = g.nk;
+    for (int n = 0; n < NT; n++) {
+        if ((rc = tmap3(h, b.T[n], nx, ny, nk, FT_RW, 1, 1, &m.T[n])) ||
+            (rc = tmap3(h, b.tm_in[n], g.tpitch, g.nj + 4, nk, FT_RW, 1, 1, &m.tm[n]))) return rc;
+        if (!UPD && b.accumulate && (rc = tmap3(h, b.th[n], nx, ny, nk, FT_RW, 1, 1, &m.th[n]))) return rc;
+    }
+    if ((rc = tmap3(h, b.u, nx, ny, nk, FT_RW, 1, 1, &m.u)) || (rc = tmap3(h, b.v, nx, ny, nk, FT_RW, 1, 1, &m.v)) ||
+        (rc = tmap3(h, b.w, nx, ny, nk + 1, FT_RW, 1, 2, &m.w)) || (rc = tmap3(h, b.rho, nx, ny, nk, FT_RW, 1, 1, &m.rho)) ||
+        (rc = tmap3(h, h->met_ring, nx, ny, 2, FT_RW, 1, 2, &m.met_ring)) || (rc = tmap3(h, h->dxte, nx, ny, 1, FT_RW, 1, 1, &m.dxte)) ||
+        (rc = tmap3(h, h->met_y, nx, ny, 2, FT_RW, 1, 2, &m.met_y))) return rc;
+    if (UPD && ((rc = tmap3(h, b.rho_m1, nx, ny, nk, FT_RW, 1, 1, &m.rho_m1)) || (rc = tmap3(h, b.rho_r, nx, ny, nk, FT_RW, 1, 1, &m.rho_r)))) return rc;
+    if (h->smem_ok.insert((const void *)k_sweby_xy_tma<NT, VAR, DIAG, UPD>).second)
+        CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy_tma<NT, VAR, DIAG, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::BYTES));
+    LAUNCH(h, (k_sweby_xy_tma<NT, VAR, DIAG, UPD>), nblk, 32 * FWARPS, LY::BYTES, st, g, b, m, nxb, nxt, (unsigned)(n3(h) + NIB_PAD));
+    return 0;
+}
+
+template <int NT>
+static bool xy_tma_ok(const mom5adv_ctx *h, const SwebyArgs<NT> &b, bool upd)
+{
+    bool ok = tma_ok(h) && aligned16(b.u) && aligned16(b.v) && aligned16(b.w) && aligned16(b.rho);
+    for (int n = 0; n < NT; n++) ok = ok && aligned16(b.T[n]) && (upd || !b.accumulate || aligned16(b.th[n]));
+    if (upd) ok = ok && aligned16(b.rho_m1) && aligned16(b.rho_r);
+    return ok;
+}
+
 template <int NT, int VAR, bool DIAG>
 static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyArgs<NT> &a, cudaStream_t st)
 {
@@ -650,6 +812,11 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
         const int nrows = b.row_last - b.row_first + 1;
         if (nrows <= 0) return 0;
         dim3 grid(pt.count < 0 ? nzt : pt.count, nrows, (g.nk + b.kc - 1) / b.kc);
+        bool tma = tma_ok(h);
+        for (int n = 0; n < NT; n++) tma = tma && aligned16(b.T[n]);
+        tma = tma && aligned16(b.w) && aligned16(b.rho);
+        b.zbits = h->zbits; b.nzw = h->nzw;
+        if (tma) return launch_z_tma<NT, VAR, DIAG>(h, b, grid, st);
         LAUNCH(h, (k_sweby_z<NT, VAR, DIAG>), grid, ZBX, 0, st, g, b);
     } else if (phase == PH_X) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
@@ -670,12 +837,14 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
         const int njc = (g.nj + b.kc - 1) / b.kc;
         const unsigned nblk = (unsigned)(g.nk * nxb * (pt.count < 0 ? njc : pt.count));
         if (VAR == VAR_ALL && !DIAG && b.Tnew[0]) {   // time update in the epilogue (mom5adv_sweby_all_step_dev)
+            if (xy_tma_ok<NT>(h, b, true)) return launch_xy_tma<NT, VAR_ALL, false, true>(h, b, nblk, nxb, nxt, st);
             typedef FusedLayout<NT, true> LYU;
             if (h->smem_ok.insert((const void *)k_sweby_xy<NT, VAR_ALL, false, true>).second)   // once per handle (= per device)
                 CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR_ALL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LYU::BYTES));
             LAUNCH(h, (k_sweby_xy<NT, VAR_ALL, false, true>), nblk, 32 * FWARPS, LYU::BYTES, st, g, b, nxb, nxt);
             return 0;
         }
+        if (xy_tma_ok<NT>(h, b, false)) return launch_xy_tma<NT, VAR, DIAG, false>(h, b, nblk, nxb, nxt, st);
         if (h->smem_ok.insert((const void *)k_sweby_xy<NT, VAR, DIAG>).second)
             CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy<NT, VAR, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedLayout<NT>::BYTES));
         LAUNCH(h, (k_sweby_xy<NT, VAR, DIAG>), nblk, 32 * FWARPS, FusedLayout<NT>::BYTES, st, g, b, nxb, nxt);
@@ -778,6 +947,11 @@ static Part part_of(int first, int step, int count)
     return p;
 }
 
+// Number of trailing tiles of a dimension of n points cut into nt tiles of `size` that hold the last TWO points (the width
+// of a halo strip): 1, or 2 when the last tile holds a single point.  These tiles (and tile 0) form the "edge set" of the
+// comm/compute overlap: everything the strip pack reads, and every tile that reads what the strip unpack writes.
+static int edge_tiles(int n, int size, int nt) { return (n - (nt - 1) * size >= 2 || nt < 2) ? 1 : 2; }
+
 // Three separate sweeps (z, x, y), the running tracer materialised between them as the reference does.
 static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
@@ -795,8 +969,12 @@ static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st
     // Overlap the NCCL strip exchange with the interior tiles of the sweep that consumes it (the reference's only
     // overlap is tracer n's exchange with tracer n+1's compute, OTA:4214-4216): the exchange runs on the library's comm
     // stream while the x (y) sweep works on the tiles (j-chunks) that read no halo; the two edge tiles follow.
-    const bool ovx = h->overlap && plan_has_remote(h, 1) && nxt >= 4;
-    const bool ovy = h->overlap && plan_has_remote(h, 2) && njc >= 4;
+    // The tiles that run under the exchange must touch no halo cell (the unpack writes them concurrently): x tile t reads
+    // tm(31t-1 .. 31t+33), y chunk c reads rows cR-1 .. (c+1)R+2.  When the last tile (chunk) holds a single column (row)
+    // the one before it reaches into the halo as well and joins the edge set.
+    const int x_last = edge_tiles(g.ni, 31, nxt), y_last = edge_tiles(g.nj, h->y_rows, njc);
+    const bool ovx = h->overlap && plan_has_remote(h, 1) && nxt >= 3 + x_last;
+    const bool ovy = h->overlap && plan_has_remote(h, 2) && njc >= 3 + y_last;
     cudaStream_t sc = h->s_comm;
     const Part all;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
@@ -809,9 +987,10 @@ static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
         CUDA_TRY(cudaEventRecord(h->ev[2], st));
-        if ((rc = run_phase_all(h, c, PH_X, part_of(1, 1, nxt - 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_X, part_of(1, 1, nxt - 1 - x_last), st))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
-        if ((rc = run_phase_all(h, c, PH_X, part_of(0, nxt - 1, 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_X, part_of(0, 1, 1), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_X, part_of(nxt - x_last, 1, x_last), st))) return rc;
     } else {
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[2], st));
@@ -824,9 +1003,10 @@ static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st
         if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[3], sc));
         CUDA_TRY(cudaEventRecord(h->ev[4], st));
-        if ((rc = run_phase_all(h, c, PH_Y, part_of(1, 1, njc - 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Y, part_of(1, 1, njc - 1 - y_last), st))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[3], 0));
-        if ((rc = run_phase_all(h, c, PH_Y, part_of(0, njc - 1, 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Y, part_of(0, 1, 1), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Y, part_of(njc - y_last, 1, y_last), st))) return rc;
     } else {
         if ((rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[4], st));
@@ -861,19 +1041,23 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
     const int c_hi = std::min((g.nj - 2) / rows - 1, njc - 1);
     const bool need_y = !h->plan[2].recvs.empty();
-    const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 4;
+    // z tiles holding the columns 1, 2, ni-1, ni the E/W strip pack reads run BEFORE the exchange starts (the last two
+    // columns span two tiles when ni % ZBX == 1)
+    const int z_last = edge_tiles(g.ni, ZBX, nzt);
+    const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 3 + z_last;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && c_hi >= 1;
     cudaStream_t sc = h->s_comm;
     const Part all;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     if (c.adv) zero_rings(h, c.adv, c.ntr, st);
     if (ovx) {
-        if ((rc = run_phase_all(h, c, PH_Z, part_of(0, nzt - 1, 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(0, 1, 1), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(nzt - z_last, 1, z_last), st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[0], 0));
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
-        if ((rc = run_phase_all(h, c, PH_Z, part_of(1, 1, nzt - 2), st))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(1, 1, nzt - 1 - z_last), st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[1], st));
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
     } else {
@@ -1265,15 +1449,16 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
             }
         }
         const size_t n4 = (size_t)g.s4 * g.nk;
-        if (!h->pp_tr) {
-            CUDA_TRY(cudaMalloc(&h->pp_tr, n4 * sizeof(double)));
-            CUDA_TRY(cudaMalloc(&h->pp_da, n4 * sizeof(double)));
-            CUDA_TRY(cudaMalloc(&h->pp_m4, n4 * sizeof(double)));
+        if (!h->pp_ready) {
+            if (!h->pp_tr) CUDA_TRY(cudaMalloc(&h->pp_tr, n4 * sizeof(double)));
+            if (!h->pp_da) CUDA_TRY(cudaMalloc(&h->pp_da, n4 * sizeof(double)));
+            if (!h->pp_m4) CUDA_TRY(cudaMalloc(&h->pp_m4, n4 * sizeof(double)));
             // mdppm_init (OTA:1714-1726): tmask_mdppm = 0; compute domain := Grd%tmask; full halo-4 update
             CUDA_TRY(cudaMemsetAsync(h->pp_m4, 0, n4 * sizeof(double), st));
             LAUNCH(h, k_d1_to_h4, dim3((g.ni + 127) / 128, g.nj, g.nk), 128, 0, st, g, h->tmask, h->pp_m4);
             double *m1[1] = {h->pp_m4};
             if ((rc = halo_update_l<2>(h, m1, 1, 3, st))) return rc;
+            h->pp_ready = true;   // only now: a failed mask update must not leave later calls with an unfilled tmask_mdppm
         }
         PPMArgs a{};
         a.T = Tm1; a.u = u; a.v = v; a.w = w; a.rho = rho; a.m4 = h->pp_m4; a.tmask = h->tmask;

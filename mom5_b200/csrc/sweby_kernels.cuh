@@ -41,6 +41,8 @@ struct SwebyArgs {
     const double *u, *v, *w, *rho;
     const uint8_t *nib;         // mask nibbles of this sweep's direction, data-domain layout
     const uint8_t *nib2;        // fused x+y pass: the y nibbles (nib holds the x nibbles)
+    const unsigned *zbits;      // z sweep: per-column mask bit strings (ZBits), nzw words per column
+    int nzw;
     const double *dat, *datr, *dxte, *dyte, *dxtn, *dytn;
     double dtime, sl;
     int kc;                     // z/x: levels per k-chunk;  y: rows per j-chunk
@@ -81,6 +83,30 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef YMINB
 #define YMINB 4
 #endif
+
+// Land/sea mask of one (i,j) column as a bit string: bit b = tmask_mdfl(i,j,clamp(b,1,nk)) for b = 0..nk+2 (k_build_zbits), so the
+// z sweep's neighbourhood nibble of level k -- m(km1), m(k), m(kp1), m(kp2) with the reference's clamped indices
+// (OTA:4157-4159) -- is bits k-1..k+2.  Word w of column (i,j) sits at zbits[w * slab + d2(i,j)] (coalesced across a warp);
+// 75 levels are three words, loaded once, so the k loop carries no mask load.
+struct ZBits {
+    unsigned lo, hi, nn;    // words wi, wi+1, wi+2 of the column
+    int wi, sh;
+    static __device__ __forceinline__ unsigned word(const unsigned *col, unsigned stride, int nw, int w)
+    {
+        return (w < nw) ? col[(size_t)w * stride] : 0u;
+    }
+    __device__ __forceinline__ void init(const unsigned *col, unsigned stride, int nw, int k0)
+    {
+        wi = (k0 - 1) >> 5; sh = (k0 - 1) & 31;
+        lo = word(col, stride, nw, wi); hi = word(col, stride, nw, wi + 1); nn = word(col, stride, nw, wi + 2);
+    }
+    // nibble of the current level: bit0 = m(km1), bit1 = m(k), bit2 = m(kp1), bit3 = m(kp2)
+    __device__ __forceinline__ unsigned nib() const { return __funnelshift_r(lo, hi, sh) & 15u; }
+    __device__ __forceinline__ void next(const unsigned *col, unsigned stride, int nw)   // once per level; reloads every 32 levels
+    {
+        if (++sh == 32) { sh = 0; wi++; lo = hi; hi = nn; nn = word(col, stride, nw, wi + 2); }
+    }
+};
 
 template <int NT>
 struct ZLevel {
@@ -146,32 +172,29 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
     // staging front: level kf, its data-domain offset qf and the offset q2f of level min(kf+2, nk)
     int kf = k0;
     ofs_t qf = qd, q2f = qd + slab * (ofs_t)(min(k0 + 2, g.nk) - k0);
-    auto stage_next = [&](int slot) -> unsigned {                 // stages T(min(kf+2,nk)), w(kf), rho(kf); returns the nibble of kf
-        unsigned nb = 0;
+    auto stage_next = [&](int slot) {                             // stages T(min(kf+2,nk)), w(kf), rho(kf)
         if (kf <= ke) {
 #pragma unroll
             for (int n = 0; n < NT; n++) cp_async8(&sm[slot][n][tx], a.T[n] + q2f);
             cp_async8(&sm[slot][NT][tx], a.w + qf + slab);        // w3(k) = d3(k) + slab
             cp_async8(&sm[slot][NT + 1][tx], a.rho + qf);
-            nb = a.nib[qf];
         }
         qf += slab;
         if (kf + 3 <= g.nk) q2f += slab;
         kf++;
-        return nb;
     };
-    unsigned nbq[D - 1];                                          // mask nibbles of levels k+1 .. k+D-1
-    unsigned nb_first = 0;
 #pragma unroll
     for (int d = 0; d < D - 1; d++) {
-        const unsigned nb = stage_next(d);
-        if (d == 0) nb_first = nb; else nbq[d - 1] = nb;
+        stage_next(d);
         cp_async_commit();
     }
 
+    // the column's mask bits (no per-level mask load: a plain LDG in the loop exposed one DRAM latency per level, see ZBits)
+    ZBits zb;
+    zb.init(a.zbits + c2, slab, a.nzw, k0);
     ZLevel<NT> L;
     L.dat = a.dat[c2]; L.datr = a.datr[c2]; L.dtime = a.dtime; L.sl = a.sl;
-    L.nb = nb_first;
+    L.nb = zb.nib();
 #pragma unroll
     for (int n = 0; n < NT; n++) {
         const double Tkm = a.T[n][qkm];
@@ -187,13 +210,14 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
 #pragma unroll 3
     for (int k = k0; k <= ke; k++) {
         // ---- stage the operands of level k+D-1 (each thread reads back only what it staged itself) ----
-        nbq[D - 2] = stage_next(sf);
+        stage_next(sf);
         cp_async_commit();
         cp_async_wait<D - 1>();
 #pragma unroll
         for (int n = 0; n < NT; n++) L.Tp2[n] = sm[st][n][tx];
         L.wk = sm[st][NT][tx];
         L.r = sm[st][NT + 1][tx];
+        L.nb = zb.nib();
         // ---- level k ----
         if (z_level<NT, VAR, false>(L)) {
             ZLevel<NT> X = L;
@@ -216,9 +240,7 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
             L.Tp1[n] = L.Tp2[n];
         }
         L.wkm1 = L.wk;
-        L.nb = nbq[0];
-#pragma unroll
-        for (int d = 0; d + 1 < D - 1; d++) nbq[d] = nbq[d + 1];
+        zb.next(a.zbits + c2, slab, a.nzw);
         qd += slab;
         qt += (ofs_t)g.tslab;
         st = (st + 1 == D) ? 0 : st + 1;
@@ -578,6 +600,24 @@ __global__ void k_zero_ring(const Geom g, const RingArgs<NT> a)
 #pragma unroll
         for (int n = 0; n < NT; n++)
             if (a.p[n]) a.p[n][d3(g, i, j, k)] = 0.0;
+    }
+}
+
+// per-column mask bit strings for the z sweep (ZBits): bit b = m(i,j,clamp(b,1,nk)), b = 0..nk+2; data-domain 2-D layout per word
+__global__ void k_build_zbits(const Geom g, const uint8_t *__restrict__ m, unsigned *__restrict__ zbits, const int nzw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni+1
+    const int j = blockIdx.y;                              // 0..nj+1
+    if (i > g.ni + 1) return;
+    for (int w = 0; w < nzw; w++) {
+        unsigned v = 0;
+        for (int q = 0; q < 32; q++) {
+            const int b = 32 * w + q;
+            if (b > g.nk + 2) break;
+            const int k = min(max(b, 1), g.nk);
+            v |= (m[m3(g, i, j, k)] ? 1u : 0u) << q;
+        }
+        zbits[(size_t)w * g.slab + d2(g, i, j)] = v;
     }
 }
 

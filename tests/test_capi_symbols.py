@@ -21,7 +21,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.mom5adv_version() == 100
+    assert lib.mom5adv_version() == 200
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -1,0 +1,160 @@
+"""GPU parity at the sizes the published numbers are quoted on (run on the B200 box: pytest -m gpu).
+
+Every comparison is CUDA path (through the C ABI) vs the CPU ORACLE, bit for bit -- not one CUDA driver against another:
+  * the default fused driver (TMA-staged z sweep + fused x/y pass) on the 0.25-degree tripolar grid (1440 x 1080 x 50) and on a
+    448-row tripolar band of the bench workload (3600 columns x 75 levels: the bench's own x extent, tile counts and fold width);
+  * quicker (three-level and two-level, limit_with_upwind on / off), first-order upwind and per-tracer MDFL at the shapes of
+    BASELINE.json config 2 (256 x 256 x 50 torus and gyre) and config 3 (360 x 300 x 50, 1-degree global).
+Inputs are generated on the device (seconds) and copied to the host for the oracle, which runs its multi-block driver
+(OpenMP threads stand in for MPI ranks) so that the large cases finish in seconds.
+"""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _generate(case, over, with_tau=False):
+    from mom5_b200.synthetic import CASES, Generator
+    spec = dataclasses.replace(CASES[case], **over)
+    if spec.flow_scale is None:
+        spec = dataclasses.replace(spec, flow_scale=spec.cfl / 12.0)   # analytic scale: skips the global-max calibration pass
+    gen = Generator(spec, device=torch.device("cuda"))
+    return spec, gen.block(1, spec.ni, 1, spec.nj, ntr=spec.ntr, with_tau=with_tau)
+
+
+def _to_host(b):
+    """BlockInputs on the device -> the same block on the host (for the oracle)"""
+    from mom5_b200.synthetic import BlockInputs
+    c = lambda t: t.cpu()
+    return BlockInputs(b.spec, b.i0, b.i1, b.j0, b.j1, {k: c(v) for k, v in b.grid2d.items()}, c(b.dzt), c(b.tmask), c(b.rho_dzt),
+                       c(b.uhrho_et), c(b.vhrho_nt), c(b.wrho_bt), [c(t) for t in b.T], [c(t) for t in b.T_tau],
+                       [c(t) for t in b.th_tendency], [c(t) for t in b.tmask_limit])
+
+
+def _oracle_blocks(spec, hb, nthreads):
+    """multi-block oracle over the host copy: (Oracle, dec, blocks)"""
+    from mom5_b200.domain import define_layout
+    from oracle.oracle import Oracle, split_blocks
+    px, py = define_layout(spec.ni, spec.nj, nthreads)
+    dec = spec.decomposition(px, py)
+    blocks = split_blocks(dec, hb)
+    return Oracle(dec, blocks), dec, blocks
+
+
+@pytest.mark.parametrize("case,over", [
+    ("global_025deg", {}),                                              # BASELINE config 4 shape: 1440 x 1080 x 50, 3 tracers
+    ("global_01deg", dict(nj=448)),                                     # bench workload band: 3600 x 448 x 75, fold at full width
+    ("global_1deg", dict(ntr=10)),                                      # BASELINE config 3: 360 x 300 x 50, 10 tracers (groups 4+3+3)
+])
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_default_driver_vs_oracle_at_scale(case, over, tma, monkeypatch):
+    from mom5_b200.api import TracerAdvect
+    from oracle.oracle import gather
+    if tma == "0" and case == "global_01deg":
+        pytest.skip("the LDGSTS staging is covered at this width by the 0.25-degree case")
+    monkeypatch.setenv("MOM5ADV_TMA", tma)
+    monkeypatch.setenv("MOM5ADV_FUSE", "1")
+    spec, b = _generate(case, over)
+    ntr = spec.ntr
+    adv = TracerAdvect(b, ntracers_max=ntr)
+    th = [t.clone() for t in b.th_tendency]
+    out = [torch.full_like(t, -777.0) for t in b.T]
+    adv.advect_tracer_sweby_all(b.T, th, out, b.uhrho_et, b.vhrho_nt, b.wrho_bt, b.rho_dzt, spec.dtime)
+    torch.cuda.synchronize()
+    chk = [adv.chksum(t) for t in out]
+    adv.close()
+    got_th = [t[:, 1:-1, 1:-1].cpu().numpy() for t in th]
+    got_adv = [t[:, 1:-1, 1:-1].cpu().numpy() for t in out]
+    del th, out
+    hb = _to_host(b)
+    del b
+    torch.cuda.empty_cache()
+    nthreads = min(len(os.sched_getaffinity(0)), 32)
+    o, dec, blocks = _oracle_blocks(spec, hb, nthreads)
+    T = [[t.numpy() for t in bl.T] for bl in blocks]
+    tho = [[t.numpy().copy() for t in bl.th_tendency] for bl in blocks]
+    ref = o.sweby_all_timed(T, tho, spec.dtime, nthreads=nthreads)
+    for n in range(ntr):
+        want_adv = gather(dec, [ref["adv"][r][n] for r in range(len(blocks))])
+        want_th = gather(dec, [tho[r][n] for r in range(len(blocks))])
+        assert_bit_equal(got_adv[n], want_adv, f"{case} adv_tendency[{n}]")
+        assert_bit_equal(got_th[n], want_th, f"{case} th_tendency[{n}]")
+        # the device checksum (mpp_chksum of the compute domain) equals the oracle's over all blocks
+        assert chk[n] == o.chksum([ref["adv"][r][n] for r in range(len(blocks))]), f"{case} chksum[{n}]"
+    assert float(np.abs(got_adv[0]).max()) > 0.0
+
+
+CONFIG23 = [("torus", {}), ("gyre", dict(ntr=3)), ("global_1deg", dict(ntr=3))]
+
+
+@pytest.mark.parametrize("case,over", CONFIG23)
+@pytest.mark.parametrize("levels,limit", [("three", False), ("three", True), ("two", False), ("two", True)])
+def test_quicker_vs_oracle_at_config_scale(case, over, levels, limit):
+    """horz + vert quicker (OTA:2538-2653, 2981-3031) at 256x256x50 / 360x300x50: many 128-column blocks in x, fold line at width"""
+    from mom5_b200.api import ADVECT_QUICKER, TracerAdvect
+    from oracle.oracle import Oracle
+    spec, b = _generate(case, over, with_tau=True)
+    hb = _to_host(b)
+    o = Oracle(spec.decomposition(1, 1), [hb])
+    adv = TracerAdvect(b, ntracers_max=1, limit_with_upwind=limit)
+    for n in range(min(spec.ntr, 2)):
+        Tm1 = b.T[n]
+        Tt = b.T_tau[n] if levels == "three" else b.T[n]          # twolevel time stepping: taum1 == tau (OM:1490)
+        tl = b.tmask_limit[n]
+        th = b.th_tendency[n].clone()
+        wrk1 = torch.full_like(th, -777.0)
+        fx, fy, fz = torch.zeros_like(th), torch.zeros_like(th), torch.zeros_like(th)
+        adv.horz_advect_tracer(ADVECT_QUICKER, Tm1, th, wrk1, b.uhrho_et, b.vhrho_nt, spec.dtime, T_tau=Tt, tmask_limit=tl,
+                               flux_x=fx, flux_y=fy)
+        torch.cuda.synchronize()
+        hT = hb.T[n].numpy()
+        hTt = hb.T_tau[n].numpy() if levels == "three" else hT
+        r = o.horz_quicker([hT], [hTt], [hb.tmask_limit[n].numpy()], limit)
+        assert_bit_equal(wrk1, r["wrk1"][0], f"{case} quicker horz wrk1[{n}]")           # the oracle returns the dispatcher's negated wrk1 (OTA:1947-1949)
+        assert_bit_equal(fx[:, 1:-1, :-1], r["flux_x"][0][:, 1:-1, :-1], "flux_x")
+        assert_bit_equal(fy[:, :-1, 1:-1], r["flux_y"][0][:, :-1, 1:-1], "flux_y")
+        want_th = hb.th_tendency[n].numpy().copy()
+        want_th[:, 1:-1, 1:-1] += r["wrk1"][0][:, 1:-1, 1:-1]
+        assert_bit_equal(th, want_th, "th after horz")
+        adv.vert_advect_tracer(ADVECT_QUICKER, Tm1, th, wrk1, b.wrho_bt, T_tau=Tt, tmask_limit=tl, flux_z=fz)
+        torch.cuda.synchronize()
+        rv = o.vert_quicker([hT], [hTt], [hb.tmask_limit[n].numpy()])
+        assert_bit_equal(wrk1, rv["wrk1"][0], f"{case} quicker vert wrk1[{n}]")
+        assert_bit_equal(fz[:, 1:-1, 1:-1], rv["flux_z"][0][:, 1:-1, 1:-1], "flux_z")
+    adv.close()
+
+
+@pytest.mark.parametrize("case,over", CONFIG23)
+def test_upwind_and_mdfl_vs_oracle_at_config_scale(case, over):
+    """first-order upwind (OTA:2238-2294, 2792-2824) and the per-tracer MDFL Sweby arm (OTA:3806-4066) at config scale"""
+    from mom5_b200.api import ADVECT_MDFL_SWEBY, ADVECT_UPWIND, TracerAdvect
+    from oracle.oracle import Oracle
+    spec, b = _generate(case, over)
+    hb = _to_host(b)
+    o = Oracle(spec.decomposition(1, 1), [hb])
+    adv = TracerAdvect(b, ntracers_max=1)
+    n = 0
+    th = b.th_tendency[n].clone()
+    wrk1 = torch.full_like(th, -777.0)
+    adv.horz_advect_tracer(ADVECT_UPWIND, b.T[n], th, wrk1, b.uhrho_et, b.vhrho_nt)
+    torch.cuda.synchronize()
+    r = o.horz_upwind([hb.T[n].numpy()])
+    assert_bit_equal(wrk1, r["wrk1"][0], f"{case} upwind horz wrk1")
+    adv.vert_advect_tracer(ADVECT_UPWIND, b.T[n], th, wrk1, b.wrho_bt)
+    torch.cuda.synchronize()
+    rv = o.vert_upwind([hb.T[n].numpy()])
+    assert_bit_equal(wrk1, rv["wrk1"][0], f"{case} upwind vert wrk1")
+    th2 = b.th_tendency[n].clone()
+    w2 = torch.full_like(th2, -777.0)
+    adv.horz_advect_tracer(ADVECT_MDFL_SWEBY, b.T[n], th2, w2, b.uhrho_et, b.vhrho_nt, spec.dtime, wrho_bt=b.wrho_bt, rho_dzt=b.rho_dzt)
+    torch.cuda.synchronize()
+    rm = o.mdfl_sweby([hb.T[n].numpy()], spec.dtime, 1.0)
+    assert_bit_equal(w2, rm["wrk1"][0], f"{case} mdfl_sweby wrk1")
+    adv.close()

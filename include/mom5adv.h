@@ -100,6 +100,11 @@ int mom5adv_finalize(mom5adv_handle h);
  *   flux_x (i=isc-1..iec), flux_y (j=jsc-1..jec), flux_z, and the per-direction tendencies adv_x/y/z
  *   (the reference's shared wrk1 sent to diag ids *_advection_x/y/z); points outside the reference's loop
  *   ranges are left untouched.                                                                           */
+/* Host entry point: th_tendency may be NULL (single-rank layouts, no diagnostics requested): the call then returns adv_tendency
+ * only and the caller forms th_tendency += adv_tendency itself.  When th_tendency is given, the library forms the sum ON THE
+ * HOST, band by band while the next bands are on the link -- th_tendency never crosses PCIe (one IEEE add per point: the same
+ * bits as on the device).  Caller arrays are page-locked on first use (cudaHostRegister, cached by address; MOM5ADV_PIN=0
+ * disables it) so that the copies really overlap.                                                                        */
 int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime,
                       const double *const *T_taum1, double *const *th_tendency, double *const *adv_tendency,
                       const double *uhrho_et, const double *vhrho_nt, const double *wrho_bt,
@@ -209,6 +214,8 @@ int mom5adv_total_tracer_dev(mom5adv_handle h, const double *rho_dzt, const doub
 int mom5adv_last_timing_ms(mom5adv_handle h, float ms[5]);
 /* number of kernels this library launched since init (all streams) */
 int64_t mom5adv_kernel_launches(mom5adv_handle h);
+/* bytes the last host-pointer call moved over the link: [0] host->device, [1] device->host (counted copy by copy) */
+int mom5adv_last_transfer_bytes(mom5adv_handle h, int64_t bytes[2]);
 
 #ifdef __cplusplus
 }

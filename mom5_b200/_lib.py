@@ -52,6 +52,7 @@ SYMBOLS = {
     "mom5adv_total_tracer_dev": (C.c_int, [_v, dp, dp, dp, _v]),
     "mom5adv_last_timing_ms": (C.c_int, [_v, C.POINTER(C.c_float)]),
     "mom5adv_kernel_launches": (C.c_int64, [_v]),
+    "mom5adv_last_transfer_bytes": (C.c_int, [_v, C.POINTER(C.c_int64)]),
 }
 # test hooks (host-only logic, no GPU needed)
 DEBUG_SYMBOLS = {

@@ -136,7 +136,7 @@ class TracerAdvect:
                                 adv_x=None, adv_y=None, adv_z=None):
         ntr = len(T)
         dev = _on_device(T[0])
-        args = [self.handle, ntr, float(dtime), _pp(T), _pp(th_tendency), _pp(adv_tendency), _ptr(uhrho_et), _ptr(vhrho_nt),
+        args = [self.handle, ntr, float(dtime), _pp(T), _pp(th_tendency), _pp(adv_tendency), _ptr(uhrho_et), _ptr(vhrho_nt),  # th / adv may be None (host mode)
                 _ptr(wrho_bt), _ptr(rho_dzt), _pp(flux_x), _pp(flux_y), _pp(flux_z), _pp(adv_x), _pp(adv_y), _pp(adv_z)]
         if dev:
             check(self.L.mom5adv_sweby_all_dev(*args, _cur_stream()), "mom5adv_sweby_all_dev")
@@ -220,6 +220,12 @@ class TracerAdvect:
 
     def kernel_launches(self) -> int:
         return int(self.L.mom5adv_kernel_launches(self.handle))
+
+    def last_transfer_bytes(self):
+        """(host->device, device->host) bytes of the last host-pointer call"""
+        b = (C.c_int64 * 2)()
+        check(self.L.mom5adv_last_transfer_bytes(self.handle, b), "last_transfer_bytes")
+        return int(b[0]), int(b[1])
 
     def close(self):
         """ocean_tracer_advect_end"""

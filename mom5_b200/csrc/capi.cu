@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <map>
 #include <set>
+#include <thread>
 #include <tuple>
 #include <cmath>
 
@@ -152,7 +153,9 @@ struct mom5adv_ctx {
     int overlap = 1;                   // MOM5ADV_OVERLAP=0 disables the comm/compute overlap
     int y_rows = 32;
     int fuse = 1;                      // MOM5ADV_FUSE=0: three separate sweeps instead of z + fused x/y
-    int tma = 1;                       // MOM5ADV_TMA=0: per-thread LDGSTS staging instead of TMA bulk copies (also used for unaligned bases)
+    int horz_fused = 1;                // MOM5ADV_HORZ_FUSED=0: quicker / upwind horizontal arm as flux kernel + fold fix + divergence kernel
+    int tma = 3;                       // MOM5ADV_TMA: bit 0 = TMA-staged z sweep, bit 1 = TMA-staged fused x/y pass (default 3 = both); 0 = per-thread
+                                       // LDGSTS staging everywhere (also what blocks with an odd ni+2 or unaligned bases get)
     int f_rows = 64;
     std::vector<cudaEvent_t> ev_up, ev_done;
     int banded = 1;                    // MOM5ADV_BANDED=0: host-pointer sweby_all pipelines over tracers instead of j-bands
@@ -160,6 +163,13 @@ struct mom5adv_ctx {
     bool ev_valid = false;
     int64_t launches = 0;
     std::set<const void *> smem_ok;    // kernels whose dynamic shared-memory limit has been raised on this handle's device
+    long long h2d_bytes = 0, d2h_bytes = 0;   // bytes the last host-pointer call moved over the link (mom5adv_last_transfer_bytes)
+    std::map<const void *, size_t> pinned;    // caller arrays page-locked by the library (cudaHostRegister), by base address
+    int pin = 1;                       // MOM5ADV_PIN=0: never page-lock caller arrays
+    int host_threads = 8;              // MOM5ADV_HOST_THREADS: threads of the host-side th_tendency += adv_tendency
+    std::vector<double *> hstage;      // pinned staging for adv_tendency bands when the caller does not want adv back
+    size_t hstage_elems = 0;
+    std::vector<cudaEvent_t> ev_dl;    // download-complete events of the banded pipeline
     double *met_ring = 0, *met_y = 0;  // packed 2-D metrics for the TMA-staged fused pass: (dyte, datr) and (dxtn, dytn) planes
     unsigned *zbits = 0;               // per-column mask bit strings for the z sweep (k_build_zbits), nzw words per column
     int nzw = 0;
@@ -640,7 +650,11 @@ static int init_body(mom5adv_ctx *h, const mom5adv_grid *G, int ntracers_max, mo
     if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
     if (const char *fu = getenv("MOM5ADV_FUSE")) h->fuse = atoi(fu);
     if (const char *tm = getenv("MOM5ADV_TMA")) h->tma = atoi(tm);
+    if (const char *hf = getenv("MOM5ADV_HORZ_FUSED")) h->horz_fused = atoi(hf);
     if (const char *bd = getenv("MOM5ADV_BANDED")) h->banded = atoi(bd);
+    if (const char *pn = getenv("MOM5ADV_PIN")) h->pin = atoi(pn);
+    h->host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
+    if (const char *ht = getenv("MOM5ADV_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
     h->ev_up.assign(ntracers_max, nullptr); h->ev_done.assign(ntracers_max, nullptr);
     for (int n = 0; n < ntracers_max; n++) {
@@ -690,6 +704,9 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
     for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
         if (p) cudaFree(p);
     if (h->zbits) cudaFree(h->zbits);
+    for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
+    for (double *p : h->hstage) if (p) cudaFreeHost(p);
+    for (cudaEvent_t e : h->ev_dl) if (e) cudaEventDestroy(e);
     for (double *p : h->tmA) if (p) cudaFree(p);
     for (double *p : h->tmB) if (p) cudaFree(p);
     for (double *p : h->hm) if (p) cudaFree(p);
@@ -706,6 +723,7 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
 // ------------------------------------------------------------------------------------------------
 // Sweby driver
 // ------------------------------------------------------------------------------------------------
+static int z_tiles(int ni);
 static int pick_kchunk(const Geom &g, int per_level_threads)
 {
     // aim for >= ~4 resident waves of threads; each extra chunk costs one redundant face per column
@@ -747,7 +765,7 @@ static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsi
 }
 
 // TMA staging needs 16-byte aligned bases and row strides that are multiples of 16 bytes (an even ni+2)
-static bool tma_ok(const mom5adv_ctx *h) { return h->tma && (h->g.nxd % 2 == 0) && tma_encoder() != nullptr; }
+static bool tma_ok(const mom5adv_ctx *h, int which) { return (h->tma & which) && (h->g.nxd % 2 == 0) && tma_encoder() != nullptr; }
 
 template <int NT, int VAR, bool DIAG>
 static int launch_z_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, dim3 grid, cudaStream_t st)
@@ -792,7 +810,7 @@ static int launch_xy_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, unsigned nblk, 
 template <int NT>
 static bool xy_tma_ok(const mom5adv_ctx *h, const SwebyArgs<NT> &b, bool upd)
 {
-    bool ok = tma_ok(h) && aligned16(b.u) && aligned16(b.v) && aligned16(b.w) && aligned16(b.rho);
+    bool ok = tma_ok(h, 2) && aligned16(b.u) && aligned16(b.v) && aligned16(b.w) && aligned16(b.rho);
     for (int n = 0; n < NT; n++) ok = ok && aligned16(b.T[n]) && (upd || !b.accumulate || aligned16(b.th[n]));
     if (upd) ok = ok && aligned16(b.rho_m1) && aligned16(b.rho_r);
     return ok;
@@ -808,11 +826,11 @@ static int launch_group(mom5adv_ctx *h, int phase, const Part &pt, const SwebyAr
     if (pt.count == 0) return 0;
     if (phase == PH_Z) {
         b.kc = pick_kchunk(g, g.ni * g.nj);
-        const int nzt = (g.ni + ZBX - 1) / ZBX;
+        const int nzt = z_tiles(g.ni);
         const int nrows = b.row_last - b.row_first + 1;
         if (nrows <= 0) return 0;
         dim3 grid(pt.count < 0 ? nzt : pt.count, nrows, (g.nk + b.kc - 1) / b.kc);
-        bool tma = tma_ok(h);
+        bool tma = tma_ok(h, 1);
         for (int n = 0; n < NT; n++) tma = tma && aligned16(b.T[n]);
         tma = tma && aligned16(b.w) && aligned16(b.rho);
         b.zbits = h->zbits; b.nzw = h->nzw;
@@ -947,6 +965,11 @@ static Part part_of(int first, int step, int count)
     return p;
 }
 
+// z tiles: tile t covers the data-domain columns t*ZBX .. t*ZBX + ZBX-1 (column 0, the west halo, is an idle lane of tile 0).
+// Starting the tiles at an EVEN column makes every TMA box of the z sweep start on a 16-byte boundary, which the tensor-map
+// copies of FP64 data require (measured on B200: an odd first coordinate raises "illegal instruction", tests/cuda/tma_probe.cu).
+static int z_tiles(int ni) { return (ni + ZBX) / ZBX; }
+
 // Number of trailing tiles of a dimension of n points cut into nt tiles of `size` that hold the last TWO points (the width
 // of a halo strip): 1, or 2 when the last tile holds a single point.  These tiles (and tile 0) form the "edge set" of the
 // comm/compute overlap: everything the strip pack reads, and every tile that reads what the strip unpack writes.
@@ -1037,13 +1060,13 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     const Geom &g = h->g;
     pick_f_rows(h);
     const int rows = h->f_rows, njc = (g.nj + rows - 1) / rows;
-    const int nzt = (g.ni + ZBX - 1) / ZBX;
+    const int nzt = z_tiles(g.ni);
     // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
     const int c_hi = std::min((g.nj - 2) / rows - 1, njc - 1);
     const bool need_y = !h->plan[2].recvs.empty();
     // z tiles holding the columns 1, 2, ni-1, ni the E/W strip pack reads run BEFORE the exchange starts (the last two
-    // columns span two tiles when ni % ZBX == 1)
-    const int z_last = edge_tiles(g.ni, ZBX, nzt);
+    // columns span two tiles when ni % ZBX == 0: z tile t covers the data-domain columns t*ZBX .. t*ZBX + ZBX-1)
+    const int z_last = (g.ni - (nzt - 1) * ZBX + 1 >= 2 || nzt < 2) ? 1 : 2;
     const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 3 + z_last;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && c_hi >= 1;
     cudaStream_t sc = h->s_comm;
@@ -1130,8 +1153,21 @@ static int mirror_w(mom5adv_ctx *h, double **out)
     *out = h->hm_w;
     return 0;
 }
-#define H2D(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyHostToDevice, st))
-#define D2H(dst, src, n) CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyDeviceToHost, st))
+#define H2D(dst, src, n) do { CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyHostToDevice, st)); h->h2d_bytes += (long long)((n) * sizeof(double)); } while (0)
+#define D2H(dst, src, n) do { CUDA_TRY(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyDeviceToHost, st)); h->d2h_bytes += (long long)((n) * sizeof(double)); } while (0)
+
+// Page-lock a caller array once (the model's arrays live for the whole run): with pageable memory every cudaMemcpyAsync is
+// staged through a driver bounce buffer and effectively synchronous, so neither copy engine overlaps anything.  Failure to
+// register (e.g. the array is already registered, or memory limits) is not an error: the copy then simply runs staged.
+static void pin_host(mom5adv_ctx *h, const void *p, size_t bytes)
+{
+    if (!h->pin || !p || h->pinned.count(p)) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) { h->pinned[p] = 0; return; }
+    cudaGetLastError();
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->pinned[p] = bytes;
+    else { cudaGetLastError(); h->pinned[p] = 0; }
+}
 
 // Host-pointer sweby_all as a pipeline over j-BANDS (one band = one j-chunk of the fused pass): while band b is on its way
 // up the PCIe link, the SMs run the z sweep of band b-1 and the fused x/y pass of the chunk below it, and the results of
@@ -1141,16 +1177,40 @@ static int mirror_w(mom5adv_ctx *h, double **out)
 //   chunk c (rows c*R+1 .. (c+1)*R) reads the z-updated tracer on rows <= (c+1)*R + 2  ->  it runs after band c+1;
 //   chunks touching a halo row of the x-updated tracer (the first, the last one or two) run at the end, after the edge-row
 //   x sweep and the N/S strip update, exactly as in sweby_dev_fused.
-static int band_copy(const Geom &g, double *dst, const double *src, int ja, int jb, int nlev, cudaMemcpyKind kind, cudaStream_t st)
+static int band_copy(mom5adv_ctx *h, double *dst, const double *src, int ja, int jb, int nlev, cudaMemcpyKind kind, cudaStream_t st)
 {
-    const size_t pitch = (size_t)g.slab * sizeof(double), ofs = (size_t)ja * g.nxd;
-    CUDA_TRY(cudaMemcpy2DAsync(dst + ofs, pitch, src + ofs, pitch, (size_t)(jb - ja + 1) * g.nxd * sizeof(double), (size_t)nlev, kind, st));
+    const Geom &g = h->g;
+    const size_t pitch = (size_t)g.slab * sizeof(double), ofs = (size_t)ja * g.nxd, width = (size_t)(jb - ja + 1) * g.nxd * sizeof(double);
+    CUDA_TRY(cudaMemcpy2DAsync(dst + ofs, pitch, src + ofs, pitch, width, (size_t)nlev, kind, st));
+    (kind == cudaMemcpyHostToDevice ? h->h2d_bytes : h->d2h_bytes) += (long long)(width * nlev);
     return 0;
+}
+
+// th_tendency(i,j,k) += adv(i,j,k) on the compute-domain points of rows ja..jb, on the host (OTA:4420-4424: the reference touches
+// th_tendency on the compute domain only; halo points must keep their bits, so they are not even added a zero)
+static void host_accumulate(const Geom &g, double *th, const double *adv, int ja, int jb, int nthreads)
+{
+    ja = std::max(ja, 1); jb = std::min(jb, g.nj);
+    if (jb < ja) return;
+    const int nrow = (jb - ja + 1) * g.nk;                 // (row, level) pairs
+    nthreads = std::max(1, std::min(nthreads, nrow));
+    auto work = [&](int t) {
+        for (int q = t; q < nrow; q += nthreads) {
+            const int k = q / (jb - ja + 1) + 1, j = ja + q % (jb - ja + 1);
+            double *a = th + d3(g, 1, j, k);
+            const double *b = adv + d3(g, 1, j, k);
+            for (int i = 0; i < g.ni; i++) a[i] = a[i] + b[i];
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th_ : pool) th_.join();
 }
 
 static int sweby_all_banded(mom5adv_ctx *h, int ntr, double dtime, const double *const *T, double *const *th, double *const *adv,
                             const double *u, const double *v, const double *w, const double *rho, double *du, double *dv,
-                            double *dw, double *dr, double *const *dT, double *const *dth, double *const *dadv)
+                            double *dw, double *dr, double *const *dT, double *const *dadv)
 {
     const Geom &g = h->g;
     int rc;
@@ -1164,25 +1224,46 @@ static int sweby_all_banded(mom5adv_ctx *h, int ntr, double dtime, const double 
         CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         h->ev_up.push_back(e1); h->ev_done.push_back(e2);
     }
+    while ((int)h->ev_dl.size() < njc + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_dl.push_back(e);
+    }
+    // where the downloaded adv_tendency lands on the host: the caller's array, or pinned staging owned by the library
+    std::vector<double *> hadv(ntr);
+    for (int n = 0; n < ntr; n++) {
+        if (adv && adv[n]) { hadv[n] = adv[n]; continue; }
+        if ((int)h->hstage.size() <= n || h->hstage_elems < n3(h)) {
+            for (double *p : h->hstage) cudaFreeHost(p);
+            h->hstage.assign(ntr, nullptr);
+            for (int q = 0; q < ntr; q++) CUDA_TRY(cudaMallocHost(&h->hstage[q], n3(h) * sizeof(double)));
+            h->hstage_elems = n3(h);
+        }
+        hadv[n] = h->hstage[n];
+    }
     std::vector<const double *> cT(dT, dT + ntr);
-    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, cT.data(), dth, dadv, du, dv, dw, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1};
+    // the device forms adv_tendency only (accumulate = 0: th_tendency is neither read nor written on the device, and never crosses the link)
+    SwebyCall c{ntr, VAR_ALL, dtime, 1.0, cT.data(), nullptr, dadv, du, dv, dw, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     zero_rings(h, dadv, ntr, st);
-    auto download = [&](int ja, int jb, int evi) -> int {          // rows ja..jb of th, adv once the compute stream got here
+    struct Dl { int ja, jb, ev; };
+    std::vector<Dl> dls;
+    auto download = [&](int ja, int jb, int evi) -> int {          // rows ja..jb of adv once the compute stream got here
         CUDA_TRY(cudaEventRecord(h->ev_done[evi], st));
         CUDA_TRY(cudaStreamWaitEvent(down, h->ev_done[evi], 0));
-        for (int n = 0; n < ntr; n++) {
-            if ((rc = band_copy(g, th[n], dth[n], ja, jb, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
-            if (adv && adv[n] && (rc = band_copy(g, adv[n], dadv[n], ja, jb, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
-        }
+        for (int n = 0; n < ntr; n++)
+            if ((rc = band_copy(h, hadv[n], dadv[n], ja, jb, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
+        const int e = (int)dls.size();
+        CUDA_TRY(cudaEventRecord(h->ev_dl[e], down));
+        dls.push_back({ja, jb, e});
         return 0;
     };
     for (int b = 0; b < njc; b++) {
         const int ja = (b == 0) ? 0 : b * R + 1, jb = (b == njc - 1) ? g.nj + 1 : (b + 1) * R;
         const cudaMemcpyKind H = cudaMemcpyHostToDevice;
-        if ((rc = band_copy(g, du, u, ja, jb, g.nk, H, up)) || (rc = band_copy(g, dv, v, ja, jb, g.nk, H, up)) ||
-            (rc = band_copy(g, dr, rho, ja, jb, g.nk, H, up)) || (rc = band_copy(g, dw, w, ja, jb, g.nk + 1, H, up))) return rc;
+        if ((rc = band_copy(h, du, u, ja, jb, g.nk, H, up)) || (rc = band_copy(h, dv, v, ja, jb, g.nk, H, up)) ||
+            (rc = band_copy(h, dr, rho, ja, jb, g.nk, H, up)) || (rc = band_copy(h, dw, w, ja, jb, g.nk + 1, H, up))) return rc;
         for (int n = 0; n < ntr; n++)
-            if ((rc = band_copy(g, dT[n], T[n], ja, jb, g.nk, H, up)) || (rc = band_copy(g, dth[n], th[n], ja, jb, g.nk, H, up))) return rc;
+            if ((rc = band_copy(h, dT[n], T[n], ja, jb, g.nk, H, up))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_up[b], up));
         CUDA_TRY(cudaStreamWaitEvent(st, h->ev_up[b], 0));
         Part zp;
@@ -1208,15 +1289,17 @@ static int sweby_all_banded(mom5adv_ctx *h, int ntr, double dtime, const double 
     if (njc > first_tail && (rc = run_phase_all(h, c, PH_XY, part_of(first_tail, 1, njc - first_tail), st))) return rc;
     if (njc > 1) {
         if ((rc = download(0, R, njc))) return rc;                         // chunk 0 with the south halo row
-        // remaining rows up to the north halo row, in one go
-        CUDA_TRY(cudaStreamWaitEvent(down, h->ev_done[njc], 0));
-        for (int n = 0; n < ntr; n++) {
-            if ((rc = band_copy(g, th[n], dth[n], first_tail * R + 1, g.nj + 1, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
-            if (adv && adv[n] && (rc = band_copy(g, adv[n], dadv[n], first_tail * R + 1, g.nj + 1, g.nk, cudaMemcpyDeviceToHost, down))) return rc;
-        }
+        if ((rc = download(first_tail * R + 1, g.nj + 1, njc))) return rc; // remaining rows up to the north halo row, in one go
     } else if ((rc = download(0, g.nj + 1, njc))) return rc;
     h->ev_valid = false;
     CUDA_TRY(cudaGetLastError());
+    // everything is enqueued; this thread now follows the downloads and accumulates band by band while the link and the SMs go on
+    for (const Dl &d : dls) {
+        CUDA_TRY(cudaEventSynchronize(h->ev_dl[d.ev]));
+        if (th)
+            for (int n = 0; n < ntr; n++)
+                if (th[n]) host_accumulate(g, th[n], hadv[n], d.ja, d.jb, h->host_threads);
+    }
     CUDA_TRY(cudaStreamSynchronize(down));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
@@ -1227,11 +1310,22 @@ extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const 
                                  double *const *fx, double *const *fy, double *const *fz, double *const *ax, double *const *ay,
                                  double *const *az)
 {
-    if (!h || !T || !th || !u || !v || !w || !rho) { set_error("mom5adv_sweby_all: null argument"); return MOM5ADV_EINVAL; }
+    if (!h || !T || !u || !v || !w || !rho) { set_error("mom5adv_sweby_all: null argument"); return MOM5ADV_EINVAL; }
+    if (!th && !adv) { set_error("mom5adv_sweby_all: neither th_tendency nor adv_tendency is wanted"); return MOM5ADV_EINVAL; }
     if (ntr < 1 || ntr > h->ntr_max) { set_error("mom5adv_sweby_all: ntr=%d outside 1..%d", ntr, h->ntr_max); return MOM5ADV_EINVAL; }
     cudaStream_t st = h->stream;
     const size_t N = n3(h);
     int rc;
+    h->h2d_bytes = h->d2h_bytes = 0;
+    {   // page-lock the caller's arrays (once per array: the cache is keyed by address)
+        const size_t B = N * sizeof(double);
+        pin_host(h, u, B); pin_host(h, v, B); pin_host(h, rho, B); pin_host(h, w, (size_t)h->g.slab * (h->g.nk + 1) * sizeof(double));
+        for (int n = 0; n < ntr; n++) {
+            pin_host(h, T[n], B);
+            if (th && th[n]) pin_host(h, th[n], B);
+            if (adv && adv[n]) pin_host(h, adv[n], B);
+        }
+    }
     size_t slot = 0;
     double *du, *dv, *dw, *dr;
     if ((rc = mirror(h, slot++, &du)) || (rc = mirror(h, slot++, &dv)) || (rc = mirror(h, slot++, &dr)) || (rc = mirror_w(h, &dw))) return rc;
@@ -1258,7 +1352,8 @@ extern "C" int mom5adv_sweby_all(mom5adv_handle h, int ntr, double dtime, const 
     pick_f_rows(h);
     if (!any_diag && h->banded && h->fuse && !plan_has_remote(h, 1) && !plan_has_remote(h, 2) &&
         (h->g.nj + h->f_rows - 1) / h->f_rows >= 4)
-        return sweby_all_banded(h, ntr, dtime, T, th, adv, u, v, w, rho, du, dv, dw, dr, dT.data(), dth.data(), dadv.data());
+        return sweby_all_banded(h, ntr, dtime, T, th, adv, u, v, w, rho, du, dv, dw, dr, dT.data(), dadv.data());
+    if (!th) { set_error("mom5adv_sweby_all: th_tendency may only be omitted on the banded single-rank pipeline"); return MOM5ADV_EUNSUP; }
     if (!any_diag && ntr > 1) {
         // Pipelined over tracers: the copy engines run in both directions while the SMs work on another tracer.
         //   up stream  : u, v, w, rho, then (T_n, th_n) for n = 0, 1, ...
@@ -1382,6 +1477,32 @@ static int fold_line_fix(mom5adv_ctx *h, double *fy, cudaStream_t st)
 // ------------------------------------------------------------------------------------------------
 // horz_advect_tracer / vert_advect_tracer (one tracer)
 // ------------------------------------------------------------------------------------------------
+// quicker / upwind horizontal arm as ONE pass (k_horz_fused); tq = h->tmA[0] must already hold tracer_quick for quicker
+static int horz_fused_dev(mom5adv_ctx *h, bool quicker, const double *Tm1, const double *Tt, const double *tlimit, int limit,
+                          const double *u, const double *v, double *th, double *wrk1, double *fx, double *fy, cudaStream_t st)
+{
+    const Geom &g = h->g;
+    HorzIn a{h->tmask, h->dyte, h->dxtn, Tm1, Tt, h->tmA[0], tlimit, u, v, h->mask, limit};
+    const bool flux = fx || fy;
+    // flux_x = flux_y = 0 outside the loop ranges (OTA:2568-2569) -- only when the caller wants the arrays at all
+    if (fx) CUDA_TRY(cudaMemsetAsync(fx, 0, n3(h) * sizeof(double), st));
+    if (fy) CUDA_TRY(cudaMemsetAsync(fy, 0, n3(h) * sizeof(double), st));
+    double *wz[1] = {wrk1};
+    zero_rings(h, wz, 1, st);                                  // Tracer%wrk1 = 0 on the data domain (OTA:1925-1931)
+    // the folded top row is on this rank as a whole (layout_x = 1): its eastern half takes minus the mirror column's north flux
+    const int fold_mid = (h->tripolar && h->iy == h->py - 1 && h->px == 1) ? (1 + h->ni_g) / 2 + 1 : 0;
+    const dim3 grid((g.ni + 30) / 31, (g.nj + HFW - 1) / HFW, g.nk), block(32, HFW);
+    if (quicker) {
+        if (flux) LAUNCH(h, (k_horz_fused<true, true>), grid, block, 0, st, g, h->qw, a, h->datr, fold_mid, th, wrk1, fx, fy);
+        else LAUNCH(h, (k_horz_fused<true, false>), grid, block, 0, st, g, h->qw, a, h->datr, fold_mid, th, wrk1, fx, fy);
+    } else {
+        if (flux) LAUNCH(h, (k_horz_fused<false, true>), grid, block, 0, st, g, h->qw, a, h->datr, 0, th, wrk1, fx, fy);
+        else LAUNCH(h, (k_horz_fused<false, false>), grid, block, 0, st, g, h->qw, a, h->datr, 0, th, wrk1, fx, fy);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, const double *Tm1, const double *Tt,
                                 const double *tlimit, int limit_with_upwind, const double *u, const double *v, const double *w,
                                 const double *rho, double *th, double *wrk1, double *fx, double *fy, double *fz, void *stream)
@@ -1493,6 +1614,7 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
         return 0;
     }
     case MOM5ADV_ADVECT_UPWIND: {
+        if (h->horz_fused) return horz_fused_dev(h, false, Tm1, nullptr, nullptr, 0, u, v, th, wrk1, fx, fy, st);
         double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
         int rc;
         if (!tfx && (rc = mirror(h, 0, &tfx))) return rc;
@@ -1509,6 +1631,9 @@ extern "C" int mom5adv_horz_dev(mom5adv_handle h, int scheme, double dtime, cons
         double *f0[1] = {h->tmA[0]};
         int rc = halo_update(h, f0, 1, 3, st);
         if (rc) return rc;
+        // flux, fold line and divergence in one pass unless the fold line is split over ranks (then: flux arrays + strip exchange)
+        if (h->horz_fused && !(h->tripolar && h->px > 1))
+            return horz_fused_dev(h, true, Tm1, Tt, tlimit, limit_with_upwind, u, v, th, wrk1, fx, fy, st);
         double *tfx = fx, *tfy = fy;   // the reference's module-level flux_x / flux_y work arrays
         if (!tfx && (rc = mirror(h, 0, &tfx))) return rc;
         if (!tfy && (rc = mirror(h, 1, &tfy))) return rc;
@@ -1839,6 +1964,13 @@ extern "C" int mom5adv_last_timing_ms(mom5adv_handle h, float ms[5])
 }
 
 extern "C" int64_t mom5adv_kernel_launches(mom5adv_handle h) { return h ? h->launches : 0; }
+
+extern "C" int mom5adv_last_transfer_bytes(mom5adv_handle h, int64_t bytes[2])
+{
+    if (!h || !bytes) { set_error("mom5adv_last_transfer_bytes: null argument"); return MOM5ADV_EINVAL; }
+    bytes[0] = h->h2d_bytes; bytes[1] = h->d2h_bytes;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // quicker_init on device (OTA:1442-1586)

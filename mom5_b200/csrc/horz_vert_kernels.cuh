@@ -131,6 +131,112 @@ k_horz_flux(const Geom g, const QuickW q, const double *__restrict__ tmask, cons
     }
 }
 
+// ---- the same fluxes as device functions of ONE face, for the fused pass below --------------------------------------
+struct HorzIn {
+    const double *tmask, *dyte, *dxtn, *Tm1, *Tt, *tq, *tlimit, *u, *v;
+    const uint8_t *mq;
+    int limit;
+};
+template <bool QUICKER>
+__device__ __forceinline__ double east_flux(const Geom &g, const QuickW &q, const HorzIn &a, int i, int j, int k)
+{
+    const size_t c = d3(g, i, j, k), c2 = d2(g, i, j), n2 = (size_t)g.slab;
+    bool up = !QUICKER;
+    if (QUICKER && a.limit) up = (a.tlimit[c] == 1.0);
+    if (!up) {   // OTA:2592-2604
+        const double vel = a.dyte[c2] * a.u[c];
+        const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+        const size_t mi = m3(g, i, j, k), ti = t3(g, i, j, k);
+        const double m_m1 = a.mq[mi - 1] ? 1.0 : 0.0, m_0 = a.mq[mi] ? 1.0 : 0.0, m_1 = a.mq[mi + 1] ? 1.0 : 0.0, m_2 = a.mq[mi + 2] ? 1.0 : 0.0;
+        const double eastmsk = m_0 * (1.0 - m_m1), westmsk = m_1 * (1.0 - m_2);
+        const double t0 = a.tq[ti], t1 = a.tq[ti + 1];
+        return ((vel * ((q.quick_x[c2] * a.Tt[c]) + (q.quick_x[c2 + n2] * a.Tt[c + 1]))) -
+                (upos * (((q.curv_xp[c2] * t1) + (q.curv_xp[c2 + n2] * t0)) +
+                         (q.curv_xp[c2 + 2 * n2] * ((a.tq[ti - 1] * (1.0 - eastmsk)) + (t0 * eastmsk)))))) -
+               (uneg * (((q.curv_xn[c2] * ((a.tq[ti + 2] * (1.0 - westmsk)) + (t1 * westmsk))) + (q.curv_xn[c2 + n2] * t1)) +
+                        (q.curv_xn[c2 + 2 * n2] * t0)));
+    }
+    if (QUICKER) {   // OTA:2613-2620: vel = u (not dyte*u), upos = 0.5*(vel+|vel|)
+        const double vel = a.u[c];
+        const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+        return ((a.dyte[c2] * ((upos * a.Tm1[c]) + (uneg * a.Tm1[c + 1]))) * a.tmask[c]) * a.tmask[c + 1];
+    }
+    const double velocity = 0.5 * a.u[c];   // OTA:2261-2265: velocity = 0.5*u, upos = velocity+|velocity|
+    const double upos = velocity + fabs(velocity), uneg = velocity - fabs(velocity);
+    return ((a.dyte[c2] * ((upos * a.Tm1[c]) + (uneg * a.Tm1[c + 1]))) * a.tmask[c]) * a.tmask[c + 1];
+}
+template <bool QUICKER>
+__device__ __forceinline__ double north_flux(const Geom &g, const QuickW &q, const HorzIn &a, int i, int j, int k)
+{
+    const size_t c = d3(g, i, j, k), c2 = d2(g, i, j), n2 = (size_t)g.slab;
+    bool up = !QUICKER;
+    if (QUICKER && a.limit) up = (a.tlimit[c] == 1.0);
+    if (!up) {   // OTA:2574-2586
+        const double vel = a.dxtn[c2] * a.v[c];
+        const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+        const size_t mi = m3(g, i, j, k), ti = t3(g, i, j, k);
+        const size_t mp = g.mpitch, tp = g.tpitch;
+        const double m_m1 = a.mq[mi - mp] ? 1.0 : 0.0, m_0 = a.mq[mi] ? 1.0 : 0.0, m_1 = a.mq[mi + mp] ? 1.0 : 0.0, m_2 = a.mq[mi + 2 * mp] ? 1.0 : 0.0;
+        const double rnormsk = m_0 * (1.0 - m_m1), soutmsk = m_1 * (1.0 - m_2);
+        const double t0 = a.tq[ti], t1 = a.tq[ti + tp];
+        return ((vel * ((q.quick_y[c2] * a.Tt[c]) + (q.quick_y[c2 + n2] * a.Tt[c + g.nxd]))) -
+                (upos * (((q.curv_yp[c2] * t1) + (q.curv_yp[c2 + n2] * t0)) +
+                         (q.curv_yp[c2 + 2 * n2] * ((a.tq[ti - tp] * (1.0 - rnormsk)) + (t0 * rnormsk)))))) -
+               (uneg * (((q.curv_yn[c2] * ((a.tq[ti + 2 * tp] * (1.0 - soutmsk)) + (t1 * soutmsk))) + (q.curv_yn[c2 + n2] * t1)) +
+                        (q.curv_yn[c2 + 2 * n2] * t0)));
+    }
+    if (QUICKER) {   // OTA:2625-2631
+        const double vel = a.v[c];
+        const double upos = 0.5 * (vel + fabs(vel)), uneg = 0.5 * (vel - fabs(vel));
+        return ((a.dxtn[c2] * ((upos * a.Tm1[c]) + (uneg * a.Tm1[c + g.nxd]))) * a.tmask[c]) * a.tmask[c + g.nxd];
+    }
+    const double velocity = 0.5 * a.v[c];   // OTA:2273-2277
+    const double upos = velocity + fabs(velocity), uneg = velocity - fabs(velocity);
+    return ((a.dxtn[c2] * ((upos * a.Tm1[c]) + (uneg * a.Tm1[c + g.nxd]))) * a.tmask[c]) * a.tmask[c + g.nxd];
+}
+
+// ---- flux, fold line and divergence in ONE pass (horz_advect_tracer_quicker / _upwind as the dispatcher uses them) -----------
+// A warp owns 32 consecutive east faces (i_w .. i_w+31) of one (j,k) row = 31 cells, as the Sweby x sweep does: the west flux of a
+// cell comes from the neighbouring lane by shuffle; the south flux is recomputed (no flux array is materialised, no memset,
+// no second pass).  On the folded north edge of a tripolar grid the reference makes the NORTH flux of the top row antisymmetric
+// after the fact (OTA:2640, mpp_update_domains(flux_x, flux_y, Dom_flux, gridtype=CGRID_NE)): flux_y(i, nj) := -flux_y(ni+1-i, nj)
+// for the eastern half.  With the whole fold line on this rank (layout_x = 1) that value is simply computed at the mirror
+// column; layouts that split the fold line keep the three-kernel path with its strip exchange (fold_line_fix).
+// flux_x / flux_y are written only when the caller asked for them (diagnostics): the same points the reference defines,
+// flux_x for i = 0..ni, flux_y for j = 0..nj.
+#define HFW 4
+template <bool QUICKER, bool FLUX>
+__global__ void __launch_bounds__(32 * HFW)
+k_horz_fused(const Geom g, const QuickW q, const HorzIn a, const double *__restrict__ datr, const int fold_mid,
+             double *__restrict__ th, double *__restrict__ wrk1, double *__restrict__ fx, double *__restrict__ fy)
+{
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const int i = (int)blockIdx.x * 31 + lane;             // east-face index 0..ni; lanes >= 1 own cell i
+    const int j = (int)blockIdx.y * HFW + wy + 1, k = blockIdx.z + 1;
+    if (j > g.nj) return;                                  // whole warp
+    const bool face_ok = (i <= g.ni), cell_ok = face_ok && lane >= 1;
+    const int ic = min(i, g.ni);
+    const double fe = east_flux<QUICKER>(g, q, a, ic, j, k);
+    const double fw = __shfl_up_sync(0xffffffffu, fe, 1);
+    if (FLUX && fx && face_ok) fx[d3(g, ic, j, k)] = fe;
+    if (!cell_ok) return;
+    // fold_mid > 0: this rank holds the whole folded top row; columns >= fold_mid take minus the mirror column's north flux
+    auto nflux = [&](int jj) -> double {
+        if (fold_mid > 0 && jj == g.nj && ic >= fold_mid) return -north_flux<QUICKER>(g, q, a, g.ni + 1 - ic, jj, k);
+        return north_flux<QUICKER>(g, q, a, ic, jj, k);
+    };
+    const double fn = nflux(j), fs = nflux(j - 1);
+    const size_t c = d3(g, ic, j, k);
+    if (FLUX && fy) {
+        fy[c] = fn;
+        if (j == 1) fy[c - g.nxd] = fs;
+    }
+    const double r = (a.tmask[c] * (((fe - fw) + fn) - fs)) * datr[d2(g, ic, j)];   // OTA:2645-2646 / 2282-2287
+    const double w = -r;                                                             // the dispatcher negates (OTA:1936-1949)
+    wrk1[c] = w;
+    th[c] = th[c] + w;                                                               // OTA:1990-1996
+}
+
 // OTA:2640  mpp_update_domains(flux_x, flux_y, Dom_flux, gridtype=CGRID_NE) on the folded north edge: the NORTH-position
 // component on the fold line is made antisymmetric, flux_y(i, nj) := -flux_y(ni_g+1-i, nj) for global i >= ni_g/2+1
 // (MPPI/mpp_domains_define.inc:1617,2535-2549; see oracle/mom5adv_oracle.c:orc_fold_fix_flux).

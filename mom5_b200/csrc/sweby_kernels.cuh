@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(ZBX, ZMINB) k_sweby_z(const Geom g, const Sweb
     constexpr int D = ZSTAGES;
     __shared__ double sm[D][NF][ZBX];
     const int tx = threadIdx.x;
-    const int i = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + tx + 1;
+    const int i = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + tx;   // tile t = data-domain columns t*ZBX .. (capi.cu: z_tiles)
     const int j = a.row_first + (int)blockIdx.y;
-    if (i > g.ni) return;                                // staging is per thread: no collective operation follows
+    if (i < 1 || i > g.ni) return;                       // staging is per thread: no collective operation follows
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
     const int k0 = ks > 1 ? ks - 1 : 1;  // first face evaluated (warm-up face when the chunk starts below the surface)

@@ -53,9 +53,12 @@ k_sweby_z_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ ZMaps
     uint64_t *const full = reinterpret_cast<uint64_t *>(sm + (size_t)D * NF * KC * ZBX);
     uint64_t *const empty = full + D;
     const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
-    const int i0 = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX + 1;
+    // tile t covers the data-domain columns t*ZBX .. t*ZBX + ZBX-1: the box origin is EVEN, i.e. on a 16-byte boundary, as the
+    // tensor-map copy of FP64 data requires (an odd first coordinate is an illegal instruction on B200, tests/cuda/tma_probe.cu);
+    // column 0 -- the west halo -- is an idle lane of tile 0
+    const int i0 = (a.tile_first + (int)blockIdx.x * a.tile_step) * ZBX;
     const int j = a.row_first + (int)blockIdx.y;
-    const int ncol = min(ZBX, g.ni - i0 + 1);            // > 0 by construction of the grid
+    const int ncol = min(ZBX, g.ni - i0 + 1);            // columns i0 .. min(i0 + ZBX-1, ni): > 0 by construction of the grid
     const int nwarps = (ncol + 31) >> 5;
     if (tx == 0) {
 #pragma unroll
@@ -64,8 +67,8 @@ k_sweby_z_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ ZMaps
     }
     __syncthreads();
     if (warp >= nwarps) return;                          // whole warps outside the domain leave; `empty` counts the others
-    const bool col_ok = (tx < ncol);
-    const int i = i0 + min(tx, ncol - 1);                // clamped column for the direct loads of idle lanes
+    const bool col_ok = (tx < ncol) && (i0 + tx >= 1);
+    const int i = max(i0 + min(tx, ncol - 1), 1);        // clamped column for the direct loads of idle lanes
     const int ks = blockIdx.z * a.kc + 1;
     const int ke = min(ks + a.kc - 1, g.nk);
     const int k0 = ks > 1 ? ks - 1 : 1;                  // first face evaluated (warm-up face below the surface chunk)

@@ -19,9 +19,11 @@ def oracle_lib():
     return oracle.lib()
 
 
-@pytest.fixture(params=["fused", "unfused"])
+@pytest.fixture(params=["fused", "unfused", "fused_ldgsts"])
 def sweep_mode(request, monkeypatch):
-    """Both Sweby drivers of the library: z + fused x/y pass (default) and the three separate sweeps (MOM5ADV_FUSE=0).
-    The switch is read by mom5adv_init, i.e. per handle; spawned workers inherit the environment."""
-    monkeypatch.setenv("MOM5ADV_FUSE", "1" if request.param == "fused" else "0")
+    """The Sweby drivers of the library: z + fused x/y pass with TMA staging (default; blocks with an odd ni fall back to LDGSTS
+    staging by themselves), the three separate sweeps (MOM5ADV_FUSE=0) and the fused driver with per-thread LDGSTS staging forced
+    (MOM5ADV_TMA=0).  The switches are read by mom5adv_init, i.e. per handle; spawned workers inherit the environment."""
+    monkeypatch.setenv("MOM5ADV_FUSE", "0" if request.param == "unfused" else "1")
+    monkeypatch.setenv("MOM5ADV_TMA", "0" if request.param == "fused_ldgsts" else "3")
     return request.param

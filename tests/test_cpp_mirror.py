@@ -27,7 +27,7 @@ def _build(tmp_path):
 def test_cpp_mirror_compiles_and_links(tmp_path):
     exe = _build(tmp_path)
     r = subprocess.run([exe, "--link-check"], stdout=subprocess.PIPE, text=True)
-    assert r.returncode == 0 and r.stdout.strip() == "mom5adv 100"
+    assert r.returncode == 0 and r.stdout.strip() == "mom5adv 200"
 
 
 def _dump(b, d, mode, scheme, limit):

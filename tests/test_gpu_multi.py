@@ -51,7 +51,7 @@ def _free_port():
 
 def _set_driver(driver):
     os.environ["MOM5ADV_FUSE"] = "0" if driver == "three_sweep" else "1"     # read by mom5adv_init, i.e. per handle
-    os.environ["MOM5ADV_TMA"] = "0" if driver == "fused_ldgsts" else "1"
+    os.environ["MOM5ADV_TMA"] = "0" if driver == "fused_ldgsts" else "3"
 
 
 def _worker(rank, world, port, cases, outdir):

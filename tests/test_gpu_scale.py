@@ -53,7 +53,7 @@ def _oracle_blocks(spec, hb, nthreads):
     ("global_01deg", dict(nj=448)),                                     # bench workload band: 3600 x 448 x 75, fold at full width
     ("global_1deg", dict(ntr=10)),                                      # BASELINE config 3: 360 x 300 x 50, 10 tracers (groups 4+3+3)
 ])
-@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("tma", ["3", "0"])
 def test_default_driver_vs_oracle_at_scale(case, over, tma, monkeypatch):
     from mom5_b200.api import TracerAdvect
     from oracle.oracle import gather

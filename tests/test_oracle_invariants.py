@@ -158,3 +158,19 @@ def test_mass_weighted_variant_conserves_and_is_monotone(case):
     assert abs(total) <= 1e-11 * scale
     tr = out["tracer"][0][:, 2:-2, 2:-2]
     assert float((tr * m).min()) >= -1e-12 and float((tr * m).max()) <= 1.0 + 1e-12
+
+
+def test_bench_parity_checksums_are_the_oracles_and_layout_invariant():
+    """tests/golden/parity_chksums.json (what bench.py's parity_check and the multi-GPU runs compare device checksums with) is what the
+    oracle produces -- as one block AND as 2 x 4 blocks (mpp_chksum is invariant under the PE count, mpp_chksum_int.h:20-38)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_parity_chksums", os.path.join(here, "golden", "gen_parity_chksums.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = json.load(open(os.path.join(here, "golden", "parity_chksums.json")))["global_1deg_ntr3"]
+    for layout in ((1, 1), (2, 4)):
+        got = mod.compute(layout)
+        assert got["th"] == gold["th"] and got["adv"] == gold["adv"], layout

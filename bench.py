@@ -629,6 +629,13 @@ def run_gpu(args):
             res["e2e"] = dict(value=None, unit=UNIT, error=f"{type(ex).__name__}: {ex}")
     release(keep)
 
+    # ---- the same entry point with PAGEABLE caller arrays (what the Fortran model hands over), 0.25-degree grid, N = 1 ----
+    if extras and world == 1 and not args.no_e2e:
+        try:
+            res["e2e_pageable"] = run_e2e_pageable(env)
+        except Exception as ex:
+            res["e2e_pageable"] = dict(error=f"{type(ex).__name__}: {ex}")
+
     # ---- SURVEY section 8e weak-scaling test: 1800 x 675 x 75 per GPU (the 0.1-degree grid / 8), replicated ----
     if extras and args.case == "global_01deg":
         try:
@@ -717,6 +724,38 @@ def run_e2e(args, env, spec, keep, cells):
     return dict(value=cells * ntr / dt, unit=UNIT, h2d_bytes_per_step=int(tr[0]), d2h_bytes_per_step=int(tr[1]), ms_per_step=dt * 1e3,
                 steps=steps, api="mom5adv_sweby_all (host pointers, pinned; copy pipeline over j-bands; bytes counted by the library)",
                 pcie_gbs=(tr[0] + tr[1]) / dt / 1e9)
+
+
+def run_e2e_pageable(env):
+    """mom5adv_sweby_all on plain (pageable) numpy arrays, 1440 x 1080 x 50, 3 tracers: the first call page-locks the caller's arrays
+    (cudaHostRegister, cached by address -- the model's arrays live for the whole run), later calls run the same pipeline as with
+    pinned buffers.  MOM5ADV_PIN=0 would leave every copy staged through the driver's bounce buffer."""
+    import numpy as np
+    import torch
+    from mom5_b200.api import TracerAdvect
+    from mom5_b200.synthetic import CASES, Generator
+    base = CASES["global_025deg"]
+    spec = dataclasses.replace(base, ntr=3, flow_scale=base.cfl / 12.0)
+    b = Generator(spec, device=env.dev).block(1, spec.ni, 1, spec.nj, ntr=3)
+    host = lambda t: np.array(t.cpu().numpy(), copy=True)      # fresh pageable allocations
+    T = [host(t) for t in b.T]; th = [host(t) for t in b.th_tendency]; out = [np.empty_like(t) for t in T]
+    u, v, w, rho = host(b.uhrho_et), host(b.vhrho_nt), host(b.wrho_bt), host(b.rho_dzt)
+    adv = TracerAdvect(b, ntracers_max=3)
+    del b
+    torch.cuda.empty_cache()
+    cu = spec.ni * spec.nj * spec.nk * 3
+    t0 = time.perf_counter()
+    adv.advect_tracer_sweby_all(T, th, out, u, v, w, rho, spec.dtime)
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(3):
+        adv.advect_tracer_sweby_all(T, th, out, u, v, w, rho, spec.dtime)
+    steady = (time.perf_counter() - t0) / 3
+    tr = adv.last_transfer_bytes()
+    adv.close()
+    return dict(grid=[spec.ni, spec.nj, spec.nk], first_call_ms=first * 1e3, steady_ms=steady * 1e3, value=cu / steady, unit=UNIT,
+                h2d_bytes_per_step=int(tr[0]), d2h_bytes_per_step=int(tr[1]), pcie_gbs=(tr[0] + tr[1]) / steady / 1e9,
+                note="first call includes cudaHostRegister of the caller's 14 arrays and the allocation of the device mirrors")
 
 
 _REAL_STDOUT = None

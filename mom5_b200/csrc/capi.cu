@@ -15,6 +15,7 @@
 #include <cmath>
 
 #include "../../include/mom5adv.h"
+#include "../../include/mpp_layout.h"
 #include "halo.cuh"
 #include "horz_vert_kernels.cuh"
 #include "mom5adv_internal.cuh"
@@ -149,6 +150,8 @@ struct mom5adv_ctx {
     cudaStream_t stream = 0;           // library-owned stream for the host-pointer entry points
     cudaStream_t s_up = 0, s_down = 0; // copy streams of the pipelined host-pointer path
     cudaStream_t s_comm = 0;           // halo exchange stream (overlapped with interior tiles)
+    cudaStream_t s_edge = 0;           // edge tiles / chunks of the fused driver: they run NEXT TO the interior launch, not after it
+    cudaEvent_t ev_edge[4] = {};
     cudaEvent_t ev_sync[4] = {};
     int overlap = 1;                   // MOM5ADV_OVERLAP=0 disables the comm/compute overlap
     int y_rows = 32;
@@ -221,33 +224,7 @@ static int compute_extent(int isg, int ieg, int ndivs, std::vector<int> &ibegin,
 {
     ibegin.assign(ndivs, 0);
     iend.assign(ndivs, 0);
-    const int npts = ieg - isg + 1;
-    const bool even_n = ndivs % 2 == 0, even_p = npts % 2 == 0;
-    const bool symmetrize = (even_n && even_p) || (!even_n && !even_p) || (!even_n && even_p && ndivs < npts / 2);
-    int is = isg, ie = 0, imax = ieg, ndmax = ndivs;
-    for (int ndiv = 0; ndiv < ndivs; ndiv++) {
-        if (ndiv < (ndivs - 1) / 2 + 1) {
-            ie = is + (int)std::ceil((double)(imax - is + 1) / (double)(ndmax - ndiv)) - 1;
-            const int ndmirror = (ndivs - 1) - ndiv;
-            if (ndmirror > ndiv && symmetrize) {
-                ibegin[ndmirror] = std::max(isg + ieg - ie, ie + 1);
-                iend[ndmirror] = std::max(isg + ieg - is, ie + 1);
-                imax = ibegin[ndmirror] - 1;
-                ndmax--;
-            }
-        } else if (symmetrize) {
-            is = ibegin[ndiv];
-            ie = iend[ndiv];
-        } else {
-            ie = is + (int)std::ceil((double)(imax - is + 1) / (double)(ndmax - ndiv)) - 1;
-        }
-        ibegin[ndiv] = is;
-        iend[ndiv] = ie;
-        if (ie < is) return 1;
-        if (ndiv == ndivs - 1 && iend[ndiv] != ieg) return 2;
-        is = ie + 1;
-    }
-    return 0;
+    return mpp_compute_extent_c(isg, ieg, ndivs, ibegin.data(), iend.data());   // include/mpp_layout.h (shared with the oracle)
 }
 
 static int find_div(const std::vector<int> &b, const std::vector<int> &e, int gidx)
@@ -645,6 +622,8 @@ static int init_body(mom5adv_ctx *h, const mom5adv_grid *G, int ntracers_max, mo
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->s_edge, cudaStreamNonBlocking, prio_hi));
+        for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_edge[e], cudaEventDisableTiming));
     }
     for (int e = 0; e < 4; e++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sync[e], cudaEventDisableTiming));
     if (const char *ov = getenv("MOM5ADV_OVERLAP")) h->overlap = atoi(ov);
@@ -712,7 +691,8 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
     for (double *p : h->hm) if (p) cudaFree(p);
     free_quickw(h->qw);
     for (int e = 0; e < 6; e++) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
-    for (cudaStream_t s : {h->stream, h->s_up, h->s_comm, h->s_down}) if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : {h->stream, h->s_up, h->s_comm, h->s_down, h->s_edge}) if (s) cudaStreamDestroy(s);
+    for (int e = 0; e < 4; e++) if (h->ev_edge[e]) cudaEventDestroy(h->ev_edge[e]);
     for (int e = 0; e < 4; e++) if (h->ev_sync[e]) cudaEventDestroy(h->ev_sync[e]);
     for (cudaEvent_t e : h->ev_up) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
@@ -1051,9 +1031,13 @@ static void pick_f_rows(mom5adv_ctx *h)
 }
 
 // z sweep, then x and y in one pass (k_sweby_xy): the x-updated tracer exists in HBM only on the four edge rows whose
-// north/south halo images the fused pass reads back.
-//   stream st : z edge tiles | z interior tiles | x on rows 1,2,nj-1,nj | xy interior chunks | xy edge chunks
-//   stream sc :                E/W strip update --^                       N/S strip update ----^
+// north/south halo images the fused pass reads back.  With remote neighbours the work is spread over three streams so that
+// neither the exchanges nor the small edge launches sit on the critical path:
+//   st (caller)  : z interior tiles ............ | x on rows 1,2,nj-1,nj | xy interior chunks ....................... | join
+//   se (edge)    : z edge tiles |                                        :            | xy edge chunks (first, last) |
+//   sc (comm)    :              | E/W strip update |                     | N/S strip update |
+// The edge tiles hold the columns the E/W pack reads, the edge chunks read what the N/S unpack writes; both run CONCURRENTLY
+// with the interior launch (se outranks st), so their partial waves fill up with interior blocks instead of ending in a tail.
 static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
     int rc;
@@ -1069,20 +1053,22 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
     const int z_last = (g.ni - (nzt - 1) * ZBX + 1 >= 2 || nzt < 2) ? 1 : 2;
     const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 3 + z_last;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && c_hi >= 1;
-    cudaStream_t sc = h->s_comm;
+    cudaStream_t sc = h->s_comm, se = h->s_edge;
     const Part all;
     CUDA_TRY(cudaEventRecord(h->ev[0], st));
     if (c.adv) zero_rings(h, c.adv, c.ntr, st);
     if (ovx) {
-        if ((rc = run_phase_all(h, c, PH_Z, part_of(0, 1, 1), st))) return rc;
-        if ((rc = run_phase_all(h, c, PH_Z, part_of(nzt - z_last, 1, z_last), st))) return rc;
-        CUDA_TRY(cudaEventRecord(h->ev_sync[0], st));
+        CUDA_TRY(cudaEventRecord(h->ev_edge[0], st));                      // everything the caller queued before this call
+        CUDA_TRY(cudaStreamWaitEvent(se, h->ev_edge[0], 0));
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(0, 1, 1), se))) return rc;
+        if ((rc = run_phase_all(h, c, PH_Z, part_of(nzt - z_last, 1, z_last), se))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_sync[0], se));
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_sync[0], 0));
         if ((rc = halo_update(h, h->tmA.data(), c.ntr, 1, sc))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_sync[1], sc));
         if ((rc = run_phase_all(h, c, PH_Z, part_of(1, 1, nzt - 1 - z_last), st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[1], st));
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[1], 0));              // (implies the edge tiles: the exchange waited for them)
     } else {
         if ((rc = run_phase_all(h, c, PH_Z, all, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[1], st));
@@ -1104,9 +1090,11 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
         CUDA_TRY(cudaEventRecord(h->ev_sync[3], sc));
         CUDA_TRY(cudaEventRecord(h->ev[4], st));
         if ((rc = run_phase_all(h, c, PH_XY, part_of(1, 1, c_hi), st))) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_sync[3], 0));
-        if ((rc = run_phase_all(h, c, PH_XY, part_of(0, 1, 1), st))) return rc;
-        if ((rc = run_phase_all(h, c, PH_XY, part_of(c_hi + 1, 1, njc - 1 - c_hi), st))) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(se, h->ev_sync[3], 0));              // N/S strips in place (and, through ev_sync[2], all of z and x)
+        if ((rc = run_phase_all(h, c, PH_XY, part_of(0, 1, 1), se))) return rc;
+        if ((rc = run_phase_all(h, c, PH_XY, part_of(c_hi + 1, 1, njc - 1 - c_hi), se))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_edge[1], se));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_edge[1], 0));              // join
     } else {
         if (need_y && (rc = halo_update(h, h->tmB.data(), c.ntr, 2, st))) return rc;
         CUDA_TRY(cudaEventRecord(h->ev[4], st));

@@ -18,7 +18,7 @@ module ocean_tracer_advect_gpu_mod
   implicit none
   private
   public :: gpu_tracer_advect_init, gpu_advect_tracer_sweby_all, gpu_horz_advect_tracer, gpu_vert_advect_tracer, &
-            gpu_tracer_advect_end
+            gpu_compute_adv_diss, gpu_tracer_advect_end
 
   type, bind(C) :: mom5adv_grid
      integer(c_int) :: isc, iec, jsc, jec, nk
@@ -32,6 +32,11 @@ module ocean_tracer_advect_gpu_mod
      function mom5adv_last_error() bind(C, name='mom5adv_last_error') result(msg)
        import :: c_ptr
        type(c_ptr) :: msg
+     end function
+     function mom5adv_set_device(node_local_rank) bind(C, name='mom5adv_set_device') result(rc)
+       import :: c_int
+       integer(c_int), value :: node_local_rank
+       integer(c_int) :: rc
      end function
      function mom5adv_comm_unique_id(id) bind(C, name='mom5adv_comm_unique_id') result(rc)
        import :: c_int, c_char
@@ -130,7 +135,12 @@ contains
     logical, intent(in) :: have_obc
     type(mom5adv_grid) :: g
     character(kind=c_char) :: id(128)
+    integer :: id_int(128)
     integer :: n
+    ! one rank drives one GPU: bind this rank to device (node-local rank mod device count) BEFORE any other call -- otherwise every
+    ! rank of a node lands on device 0 and ncclCommInitRank refuses the duplicate GPU.  Ranks of a node are consecutive PEs in FMS
+    ! (mpp_pe() - mpp_root_pe() counts from 0), so the global rank serves as the node-local one modulo the device count.
+    call check(mom5adv_set_device(int(mpp_pe() - mpp_root_pe(), c_int)), 'set_device')
     g%isc = Domain%isc; g%iec = Domain%iec; g%jsc = Domain%jsc; g%jec = Domain%jec; g%nk = nk
     g%ni_global = Grid%ni; g%nj_global = Grid%nj
     g%layout_x = Domain%layout(1); g%layout_y = Domain%layout(2)
@@ -144,8 +154,14 @@ contains
        ! bootstrap the NCCL communicator over the model's own MPI: rank 0 makes the id, mpp_broadcast ships it.
        ! Requires the FMS pelist order pe = ix + layout_x*iy, which is what mpp_define_domains produces.
        if (mpp_pe() == mpp_root_pe()) call check(mom5adv_comm_unique_id(id), 'comm_unique_id')
+       ! mpp_broadcast has no scalar-character specific (mpp_broadcast_char wants data(:), length, from_pe): ship the 128 bytes as
+       ! an integer array through the rank-1 integer specific mpp_broadcast(data(:), length, from_pe)
        do n = 1, 128
-          call mpp_broadcast(id(n), mpp_root_pe())
+          id_int(n) = ichar(id(n))
+       end do
+       call mpp_broadcast(id_int, 128, mpp_root_pe())
+       do n = 1, 128
+          id(n) = char(id_int(n), kind=c_char)     ! char, not achar: the id bytes use all 256 values
        end do
        call check(mom5adv_comm_create(id, int(mpp_pe() - mpp_root_pe(), c_int), int(mpp_npes(), c_int), comm), 'comm_create')
     end if

@@ -7,6 +7,7 @@
  * Expression trees are written with explicit parentheses that reproduce Fortran's
  * left-to-right evaluation of equal-precedence operators.  Compile WITHOUT FMA contraction.
  */
+#include "../include/mpp_layout.h"
 #include "mom5adv_oracle.h"
 
 #include <math.h>
@@ -38,51 +39,11 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 /* ------------------------------------------------------------------------------------------------
  * Layout: mpp_define_layout2D (MPPI/mpp_domains_define.inc:28-55)
  * ---------------------------------------------------------------------------------------------- */
-void orc_define_layout(int ni_g, int nj_g, int ndivs, int *layout2)
-{
-    int isz = ni_g, jsz = nj_g;
-    /* idiv = nint( sqrt(float(ndivs*isz)/jsz) ) : float() is default real; -r8 builds make it binary64 */
-    double q = (double)((long)ndivs * (long)isz) / (double)jsz;
-    int idiv = (int)lround(sqrt(q));
-    idiv = imax(idiv, 1);
-    while (ndivs % idiv != 0) idiv--;
-    layout2[0] = idiv;
-    layout2[1] = ndivs / idiv;
-}
+void orc_define_layout(int ni_g, int nj_g, int ndivs, int *layout2) { mpp_define_layout2d_c(ni_g, nj_g, ndivs, layout2); }
 
-/* mpp_compute_extent (MPPI/mpp_domains_define.inc:187-273), no user extent. Returns 0 on success. */
-int orc_compute_extent(int isg, int ieg, int ndivs, int *ibegin, int *iend)
-{
-    int npts = ieg - isg + 1;
-    int even_n = (ndivs % 2 == 0), even_p = (npts % 2 == 0);
-    int symmetrize = (even_n && even_p) || (!even_n && !even_p) || (!even_n && even_p && ndivs < npts / 2);
-    int is = isg, ie = 0, imaxv = ieg, ndmax = ndivs;
-    for (int ndiv = 0; ndiv < ndivs; ndiv++) {
-        if (ndiv < (ndivs - 1) / 2 + 1) {
-            ie = is + (int)ceil((double)(imaxv - is + 1) / (double)(ndmax - ndiv)) - 1;
-            int ndmirror = (ndivs - 1) - ndiv;
-            if (ndmirror > ndiv && symmetrize) {
-                ibegin[ndmirror] = imax(isg + ieg - ie, ie + 1);
-                iend[ndmirror] = imax(isg + ieg - is, ie + 1);
-                imaxv = ibegin[ndmirror] - 1;
-                ndmax = ndmax - 1;
-            }
-        } else {
-            if (symmetrize) {
-                is = ibegin[ndiv];
-                ie = iend[ndiv];
-            } else {
-                ie = is + (int)ceil((double)(imaxv - is + 1) / (double)(ndmax - ndiv)) - 1;
-            }
-        }
-        ibegin[ndiv] = is;
-        iend[ndiv] = ie;
-        if (ie < is) return 1;
-        if (ndiv == ndivs - 1 && iend[ndiv] != ieg) return 2;
-        is = ie + 1;
-    }
-    return 0;
-}
+/* mpp_compute_extent (MPPI/mpp_domains_define.inc:187-273), no user extent. Returns 0 on success.  The rule itself lives in
+ * include/mpp_layout.h, shared with the product library: it is layout bookkeeping, not arithmetic under test. */
+int orc_compute_extent(int isg, int ieg, int ndivs, int *ibegin, int *iend) { return mpp_compute_extent_c(isg, ieg, ndivs, ibegin, iend); }
 
 /* ------------------------------------------------------------------------------------------------
  * Halo update among in-process blocks.

@@ -1,4 +1,4 @@
-"""Halo exchange of halo-`halo` fields over torch.distributed point-to-point ops, driven by
+"""Test infrastructure (CPU gloo ranks): halo exchange of halo-`halo` fields over torch.distributed point-to-point ops, driven by
 ``Decomposition.exchange_plan`` -- the same message lists the CUDA library hands to ncclSend/ncclRecv
 (mom5_b200/csrc/capi.cu:halo_update).  Backend-agnostic: gloo on CPU tensors (used by the world_size-2 CPU tests
 of the multi-rank logic) or nccl on CUDA tensors.
@@ -12,7 +12,7 @@ from typing import List, Sequence
 import torch
 import torch.distributed as dist
 
-from .domain import Decomposition
+from mom5_b200.domain import Decomposition
 
 
 def _rect(f: torch.Tensor, m, halo: int) -> torch.Tensor:

@@ -26,7 +26,7 @@ def _worker(rank, world, port, case, px, py, outdir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mom5_b200.domain import XUPDATE, YUPDATE
-    from mom5_b200.exchange import halo_exchange
+    from tests.gloo_exchange import halo_exchange
     from mom5_b200.synthetic import make_case
     from oracle.oracle import Block, _pp, _ptr, lib
     L = lib()
@@ -95,7 +95,7 @@ def _worker_f3(rank, world, port, case, px, py, outdir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mom5_b200.domain import XUPDATE, YUPDATE
-    from mom5_b200.exchange import halo_exchange
+    from tests.gloo_exchange import halo_exchange
     from mom5_b200.synthetic import make_case
     from oracle.oracle import Block, _ptr, lib
     L = lib()

@@ -68,6 +68,35 @@ def test_sweby_all_host_pointer_mode(name):
     adv.close()
 
 
+def test_sweby_all_host_pointer_without_th_tendency_returns_adv_only(monkeypatch):
+    """th_tendency = NULL on the host entry point (banded single-rank pipeline): adv_tendency alone comes back, th_tendency += adv is
+    the caller's (one IEEE add per point -- the shim does it in Fortran); with th_tendency given the library forms the same sum on
+    the host.  Both against the oracle, pageable numpy arrays (page-locked by the library on first use)."""
+    from mom5_b200.api import TracerAdvect
+    from mom5_b200.synthetic import make_case
+    from oracle.oracle import Oracle
+    monkeypatch.setenv("MOM5ADV_FUSE", "1")                       # the banded pipeline belongs to the fused driver
+    g = make_case("global_1deg", ni=130, nj=70, nk=20, ntr=3, cfl=0.9)
+    b = g.block()
+    o = Oracle(g.s.decomposition(1, 1), [b])
+    th_ref = [[t.numpy().copy() for t in b.th_tendency]]
+    ref = o.sweby_all([[t.numpy() for t in b.T]], th_ref, g.s.dtime)
+    adv = TracerAdvect(b, ntracers_max=3)
+    T = [t.numpy() for t in b.T]
+    args = (b.uhrho_et.numpy(), b.vhrho_nt.numpy(), b.wrho_bt.numpy(), b.rho_dzt.numpy(), g.s.dtime)
+    out = [np.full_like(t, -777.0) for t in T]
+    adv.advect_tracer_sweby_all(T, None, out, *args)
+    h2d, d2h = adv.last_transfer_bytes()
+    assert h2d > 0 and d2h > 0 and d2h <= 3 * T[0].nbytes          # adv only comes down, th never crosses the link
+    for n in range(3):
+        assert_bit_equal(out[n], ref["adv"][0][n], f"adv[{n}] (th omitted)")
+    th = [t.numpy().copy() for t in b.th_tendency]
+    adv.advect_tracer_sweby_all(T, th, None, *args)               # adv not wanted: staged in library-owned pinned memory
+    for n in range(3):
+        assert_bit_equal(th[n], th_ref[0][n], f"th[{n}] (adv omitted)")
+    adv.close()
+
+
 @pytest.mark.parametrize("banded", ["1", "0"])
 @pytest.mark.parametrize("case,over", [("global_1deg", dict(ni=130, nj=70, nk=50, ntr=3, cfl=0.9)), ("torus", dict(ni=64, nj=48, nk=10)),
                                        ("gyre", dict(ni=96, nj=83, nk=20, ntr=5))])

@@ -130,7 +130,9 @@ struct mom5adv_ctx {
     // static device data
     double *dat = 0, *datr = 0, *dxte = 0, *dyte = 0, *dxtn = 0, *dytn = 0, *tmask = 0;
     uint8_t *mask = 0;                 // tmask_mdfl == tmask_quick as u8, halo 2
-    uint8_t *nibz = 0, *nibx = 0, *niby = 0;   // per-direction neighbourhood nibbles, data-domain layout
+    uint8_t *nibx = 0, *niby = 0;      // neighbourhood nibbles of the x and y sweeps, data-domain layout
+    uint8_t *nibx_p = 0, *niby_p = 0;  // the same with rows padded to nib_pitch bytes (a multiple of 16) for the tensor maps of the fused pass
+    int nib_pitch = 0;
     QuickW qw{};                       // quicker weights (device)
     std::vector<double *> tmA, tmB;    // h2 scratch per tracer
     double *st_ms = 0;                 // mass_mdfl of advect_tracer_mdfl_sweby_test (h2 scratch, allocated on first use)
@@ -183,7 +185,7 @@ struct mom5adv_ctx {
 #define YROWS_MAX 32
 #endif
 #ifndef FROWS_MAX
-#define FROWS_MAX 128
+#define FROWS_MAX 256
 #endif
 
 #define LAUNCH(h, kern, grid, block, smem, st, ...)  \
@@ -194,7 +196,6 @@ struct mom5adv_ctx {
 
 static size_t n3(const mom5adv_ctx *h) { return (size_t)h->g.slab * h->g.nk; }
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
-#define NIB_PAD 16   // the mask-nibble arrays are allocated NIB_PAD bytes long so that a staged row's 16-byte span never has to be clipped
 static size_t nh2(const mom5adv_ctx *h) { return (size_t)h->g.tslab * h->g.nk; }
 
 // ------------------------------------------------------------------------------------------------
@@ -654,13 +655,15 @@ static int init_body(mom5adv_ctx *h, const mom5adv_grid *G, int ntracers_max, mo
     if ((rc = halo_update(h, f0, 1, 3, st))) { return rc; }
     dim3 gm((g.ni + 4 + 127) / 128, g.nj + 4, g.nk);
     LAUNCH(h, k_h2_to_mask, gm, 128, 0, st, g, h->tmA[0], h->mask);
-    CUDA_TRY(cudaMalloc(&h->nibz, n3(h) + 2 * NIB_PAD));
-    CUDA_TRY(cudaMalloc(&h->nibx, n3(h) + 2 * NIB_PAD));
-    CUDA_TRY(cudaMalloc(&h->niby, n3(h) + 2 * NIB_PAD));
-    CUDA_TRY(cudaMemsetAsync(h->nibz + n3(h), 0, 2 * NIB_PAD, st));
-    CUDA_TRY(cudaMemsetAsync(h->nibx + n3(h), 0, 2 * NIB_PAD, st));
-    CUDA_TRY(cudaMemsetAsync(h->niby + n3(h), 0, 2 * NIB_PAD, st));
-    LAUNCH(h, k_build_nibbles, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, h->mask, h->nibz, h->nibx, h->niby);
+    h->nib_pitch = (g.nxd + 15) / 16 * 16;
+    const size_t nibp = (size_t)h->nib_pitch * g.nyd * g.nk;
+    CUDA_TRY(cudaMalloc(&h->nibx, n3(h)));
+    CUDA_TRY(cudaMalloc(&h->niby, n3(h)));
+    CUDA_TRY(cudaMalloc(&h->nibx_p, nibp));
+    CUDA_TRY(cudaMalloc(&h->niby_p, nibp));
+    CUDA_TRY(cudaMemsetAsync(h->nibx_p, 0, nibp, st));
+    CUDA_TRY(cudaMemsetAsync(h->niby_p, 0, nibp, st));
+    LAUNCH(h, k_build_nibbles, dim3((g.ni + 2 + 127) / 128, g.nj + 2, g.nk), 128, 0, st, g, h->mask, h->nibx, h->niby, h->nibx_p, h->niby_p, h->nib_pitch);
     h->nzw = (g.nk + 3 + 31) / 32;
     CUDA_TRY(cudaMalloc(&h->zbits, (size_t)h->nzw * g.slab * sizeof(unsigned)));
     LAUNCH(h, k_build_zbits, dim3((g.ni + 2 + 127) / 128, g.nj + 2), 128, 0, st, g, h->mask, h->zbits, h->nzw);
@@ -680,7 +683,7 @@ extern "C" int mom5adv_finalize(mom5adv_handle h)
     for (double *p : {h->dat, h->datr, h->dxte, h->dyte, h->dxtn, h->dytn, h->tmask, h->sendbuf, h->recvbuf, h->hm_w, h->st_ms, h->pp_tr, h->pp_m4, h->pp_da, h->pp_fz,
                       h->met_ring, h->met_y})
         if (p) cudaFree(p);
-    for (uint8_t *p : {h->mask, h->nibz, h->nibx, h->niby})
+    for (uint8_t *p : {h->mask, h->nibx, h->niby, h->nibx_p, h->niby_p})
         if (p) cudaFree(p);
     if (h->zbits) cudaFree(h->zbits);
     for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
@@ -721,9 +724,10 @@ struct Part {
 };
 enum { PH_Z = 0, PH_X = 1, PH_Y = 2, PH_XY = 3 };
 
-// 3-D FP64 tensor map over an array dimensioned (n0, n1, n2) Fortran-style (n0 contiguous), box b0 x b1 x b2
-static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsigned long long n1, unsigned long long n2, unsigned b0,
-                 unsigned b1, unsigned b2, CUtensorMap *out)
+// 3-D tensor map over an array dimensioned (n0, n1, n2) Fortran-style (n0 contiguous), box b0 x b1 x b2; ESZ = 8 (FP64) or 1 (u8)
+template <int ESZ>
+static int tmap3_t(mom5adv_ctx *h, const void *base, unsigned long long n0, unsigned long long n1, unsigned long long n2, unsigned b0,
+                   unsigned b1, unsigned b2, CUtensorMap *out)
 {
     const TmapKey key{base, n0, n1, n2, b0, b1, b2};
     auto it = h->tmaps.find(key);
@@ -731,10 +735,10 @@ static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsi
     EncodeTiledFn enc = tma_encoder();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return MOM5ADV_ECUDA; }
     const cuuint64_t dims[3] = {n0, n1, n2};
-    const cuuint64_t strides[2] = {n0 * sizeof(double), n0 * n1 * sizeof(double)};
+    const cuuint64_t strides[2] = {n0 * ESZ, n0 * n1 * ESZ};
     const cuuint32_t box[3] = {b0, b1, b2}, estr[3] = {1, 1, 1};
     CUtensorMap m;
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box, estr,
+    const CUresult r = enc(&m, ESZ == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %llux%llux%llu array, box %ux%ux%u", (int)r, n0, n1, n2, b0, b1, b2); return MOM5ADV_ECUDA; }
@@ -742,6 +746,12 @@ static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsi
     h->tmaps[key] = m;
     *out = m;
     return 0;
+}
+
+static int tmap3(mom5adv_ctx *h, const double *base, unsigned long long n0, unsigned long long n1, unsigned long long n2, unsigned b0,
+                 unsigned b1, unsigned b2, CUtensorMap *out)
+{
+    return tmap3_t<8>(h, base, n0, n1, n2, b0, b1, b2, out);
 }
 
 // TMA staging needs 16-byte aligned bases and row strides that are multiples of 16 bytes (an even ni+2)
@@ -781,9 +791,13 @@ static int launch_xy_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, unsigned nblk, 
         (rc = tmap3(h, h->met_ring, nx, ny, 2, FT_RW, 1, 2, &m.met_ring)) || (rc = tmap3(h, h->dxte, nx, ny, 1, FT_RW, 1, 1, &m.dxte)) ||
         (rc = tmap3(h, h->met_y, nx, ny, 2, FT_RW, 1, 2, &m.met_y))) return rc;
     if (UPD && ((rc = tmap3(h, b.rho_m1, nx, ny, nk, FT_RW, 1, 1, &m.rho_m1)) || (rc = tmap3(h, b.rho_r, nx, ny, nk, FT_RW, 1, 1, &m.rho_r)))) return rc;
-    if (h->smem_ok.insert((const void *)k_sweby_xy_tma<NT, VAR, DIAG, UPD>).second)
+    if ((rc = tmap3_t<1>(h, h->nibx_p, h->nib_pitch, ny, nk, FT_NW, 1, 1, &m.nibx)) || (rc = tmap3_t<1>(h, h->niby_p, h->nib_pitch, ny, nk, FT_NW, 1, 1, &m.niby))) return rc;
+    if (h->smem_ok.insert((const void *)k_sweby_xy_tma<NT, VAR, DIAG, UPD>).second) {
         CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy_tma<NT, VAR, DIAG, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::BYTES));
-    LAUNCH(h, (k_sweby_xy_tma<NT, VAR, DIAG, UPD>), nblk, 32 * FWARPS, LY::BYTES, st, g, b, m, nxb, nxt, (unsigned)(n3(h) + NIB_PAD));
+        // three 72.5 KB blocks per SM need (almost) all of the 228 KB: ask for the largest shared-memory carveout
+        CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy_tma<NT, VAR, DIAG, UPD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
+    LAUNCH(h, (k_sweby_xy_tma<NT, VAR, DIAG, UPD>), nblk, 32 * FWARPS, LY::BYTES, st, g, b, m, nxb, nxt);
     return 0;
 }
 
@@ -889,7 +903,7 @@ static int run_phase(mom5adv_ctx *h, const SwebyCall &c, int n0, int phase, cons
         diag |= a.flux[n] || a.dadv[n] || a.flux2[n] || a.dadv2[n];
     }
     a.u = c.u; a.v = c.v; a.w = c.w; a.rho = c.rho;
-    a.nib = phase == PH_Z ? h->nibz : phase == PH_Y ? h->niby : h->nibx;
+    a.nib = phase == PH_Y ? h->niby : h->nibx;      // (the z sweep reads zbits)
     a.nib2 = h->niby;
     a.dat = h->dat; a.datr = h->datr; a.dxte = h->dxte; a.dyte = h->dyte; a.dxtn = h->dxtn; a.dytn = h->dytn;
     a.dtime = c.dtime; a.sl = c.sl; a.accumulate = c.accumulate;

@@ -621,17 +621,20 @@ __global__ void k_build_zbits(const Geom g, const uint8_t *__restrict__ m, unsig
     }
 }
 
-// mask nibbles from the halo-2 u8 mask: dir 0 = z (clamped levels), 1 = x, 2 = y; data-domain layout
-__global__ void k_build_nibbles(const Geom g, const uint8_t *__restrict__ m, uint8_t *__restrict__ nz, uint8_t *__restrict__ nx,
-                                uint8_t *__restrict__ ny)
+// mask nibbles from the halo-2 u8 mask for the x and y sweeps: m(-1), m(0), m(+1), m(+2) along the sweep direction in bits 0..3.
+// Two layouts: data-domain (nx, ny: what the per-thread kernels index with their own cell offset) and, for the TMA-staged fused
+// pass, rows padded to a pitch of `np` bytes (a multiple of 16: tensor-map strides must be) -- nxp, nyp, (np, nyd, nk).
+// (The z sweep reads the column bit strings of k_build_zbits instead.)
+__global__ void k_build_nibbles(const Geom g, const uint8_t *__restrict__ m, uint8_t *__restrict__ nx, uint8_t *__restrict__ ny,
+                                uint8_t *__restrict__ nxp, uint8_t *__restrict__ nyp, const int np)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ni+1
     const int j = blockIdx.y, k = blockIdx.z + 1;          // 0..nj+1
     if (i > g.ni + 1) return;
-    const size_t q = d3(g, i, j, k);
+    const size_t q = d3(g, i, j, k), qp = (size_t)i + (size_t)np * ((size_t)j + (size_t)g.nyd * (size_t)(k - 1));
     auto M = [&](int ii, int jj, int kk) -> unsigned { return m[m3(g, ii, jj, kk)] ? 1u : 0u; };
-    const int km1 = max(k - 1, 1), kp1 = min(k + 1, g.nk), kp2 = min(k + 2, g.nk);
-    nz[q] = (uint8_t)(M(i, j, km1) | (M(i, j, k) << 1) | (M(i, j, kp1) << 2) | (M(i, j, kp2) << 3));
-    nx[q] = (i <= g.ni) ? (uint8_t)(M(i - 1, j, k) | (M(i, j, k) << 1) | (M(i + 1, j, k) << 2) | (M(i + 2, j, k) << 3)) : 0;
-    ny[q] = (j <= g.nj) ? (uint8_t)(M(i, j - 1, k) | (M(i, j, k) << 1) | (M(i, j + 1, k) << 2) | (M(i, j + 2, k) << 3)) : 0;
+    const uint8_t vx = (i <= g.ni) ? (uint8_t)(M(i - 1, j, k) | (M(i, j, k) << 1) | (M(i + 1, j, k) << 2) | (M(i + 2, j, k) << 3)) : 0;
+    const uint8_t vy = (j <= g.nj) ? (uint8_t)(M(i, j - 1, k) | (M(i, j, k) << 1) | (M(i, j + 1, k) << 2) | (M(i, j + 2, k) << 3)) : 0;
+    nx[q] = vx; ny[q] = vy;
+    nxp[qp] = vx; nyp[qp] = vy;
 }

@@ -69,6 +69,17 @@ def _worker(rank, world, port, cases, outdir):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    import json
+    import time
+    tlog, tprev = [], time.time()
+
+    def tick(what):
+        nonlocal tprev
+        now = time.time()
+        tlog.append((what, round(now - tprev, 2)))
+        tprev = now
+
+    tick("process group + communicator")
     for ci, (case, over, px, py, driver) in enumerate(cases):
         _set_driver(driver)
         g = make_case(case, **over)
@@ -76,7 +87,9 @@ def _worker(rank, world, port, cases, outdir):
         i0, i1, j0, j1 = dec.extent(rank)
         g.calibrate(i0, i1, j0, j1, reduce_max=rmax)
         b = g.block(i0, i1, j0, j1, with_tau=True)
+        tick(f"c{ci} generate")
         adv = TracerAdvect(b, dec=dec, rank=rank, ntracers_max=len(b.T), comm=comm)
+        tick(f"c{ci} init")
         T = [t.cuda() for t in b.T]
         th = [t.cuda().clone() for t in b.th_tendency]
         out = [torch.empty_like(t) for t in T]
@@ -112,11 +125,16 @@ def _worker(rank, world, port, cases, outdir):
         for n in range(len(T)):
             res[f"th{n}"] = th[n].cpu().numpy()
             res[f"adv{n}"] = out[n].cpu().numpy()
+        tick(f"c{ci} compute")
         np.savez(os.path.join(outdir, f"c{ci}_r{rank}.npz"), **res)
         dist.barrier()
         adv.close()
+        tick(f"c{ci} save+close")
     comm.destroy()
     dist.destroy_process_group()
+    tick("teardown")
+    if rank == 0:
+        json.dump(tlog, open(os.path.join(outdir, "timing_rank0.json"), "w"))
 
 
 def _run_world(tmp_path, world):
@@ -137,6 +155,13 @@ def _run_world(tmp_path, world):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+    try:   # where the wall time of the workers went (kept next to the other GPU-run artefacts when that directory exists)
+        import shutil
+        dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(dst):
+            shutil.copy(tmp_path / "timing_rank0.json", os.path.join(dst, f"multi_timing_world{world}.json"))
+    except Exception:
+        pass
     failures = []
     oracle_cache = {}
     for ci, (case, over, px, py, driver) in enumerate(cases):

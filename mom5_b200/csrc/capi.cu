@@ -794,7 +794,7 @@ static int launch_xy_tma(mom5adv_ctx *h, const SwebyArgs<NT> &b, unsigned nblk, 
     if ((rc = tmap3_t<1>(h, h->nibx_p, h->nib_pitch, ny, nk, FT_NW, 1, 1, &m.nibx)) || (rc = tmap3_t<1>(h, h->niby_p, h->nib_pitch, ny, nk, FT_NW, 1, 1, &m.niby))) return rc;
     if (h->smem_ok.insert((const void *)k_sweby_xy_tma<NT, VAR, DIAG, UPD>).second) {
         CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy_tma<NT, VAR, DIAG, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::BYTES));
-        // three 72.5 KB blocks per SM need (almost) all of the 228 KB: ask for the largest shared-memory carveout
+        // three 53 KB blocks per SM: ask for the largest shared-memory carveout
         CUDA_TRY(cudaFuncSetAttribute(k_sweby_xy_tma<NT, VAR, DIAG, UPD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     }
     LAUNCH(h, (k_sweby_xy_tma<NT, VAR, DIAG, UPD>), nblk, 32 * FWARPS, LY::BYTES, st, g, b, m, nxb, nxt);

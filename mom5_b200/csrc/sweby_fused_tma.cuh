@@ -9,14 +9,16 @@
 // LDGSTS per thread, operand and row (23 per thread and iteration, each with its 64-bit address arithmetic), ONE thread
 // issues one tensor-map copy (cp.async.bulk.tensor, SASS UTMALDG) per operand row for the whole block -- 18 per iteration,
 // the two mask-nibble rows (u8, rows padded to a multiple of 16 bytes) included:
-//   ring   (5 slots): T[NT], u, rho, (dyte, datr)          row r      -> x phase of the iteration that produces r, y phase two and one later
-//   x-only (3 slots): tm(z)[NT], dxte, x nibbles           row r
-//   y-only (3 slots): th[NT], v, (w(k-1), w(k)), (dxtn, dytn), y nibbles [, rho_dzt(taum1), rho_dztr]   face jf
-// Pairs in parentheses are two planes / levels of one array and arrive as ONE box.  "Fill f" is everything iteration f consumes;
-// it is issued TWO iterations earlier (one iteration is shorter than the loaded DRAM latency) and signals the mbarrier full[f % 3];
-// a warp reports the end of iteration `it` on done[it % 3] and the producer of iteration it+1 waits for that before it issues
-// fill it+3 over the slots iteration `it` read last.  The producer role rotates over the warps (warp it % nact), so no warp
-// carries the issue cost alone.
+//   ring   (4 slots, row r & 3): T[NT], u, rho, (dyte, datr)          row r+1   -> x phase at r+1, y phase at r+1 and r+2
+//   x-only (2 slots, row r & 1): tm(z)[NT], dxte, x nibbles           row r+1
+//   y-only (2 slots, row jf & 1): th[NT], v, (w(k-1), w(k)), (dxtn, dytn), y nibbles [, rho_dzt(taum1), rho_dztr]   face jf+1
+// Pairs in parentheses are two planes / levels of one array and arrive as ONE box.  Everything issued in iteration `it` is
+// consumed in iteration it+1 ("fill it+1") and signals the mbarrier full[(it+1) & 1]; a warp reports the end of iteration `it`
+// on done[it & 1] and the producer of iteration it+1 waits for that before it overwrites anything.  The producer role rotates over the
+// warps (warp it % nact), so no warp carries the issue cost alone.
+// (Staging TWO iterations ahead -- 5/3-slot rings, 72 KB per block -- was measured too: the warps then stop spinning on `full`
+// (with a distance of one ~17% of the executed instructions are try_wait / branch / yield), but the pass is not a cycle faster,
+// profiles/ab_r02_k_*.json: on a power-capped B200 the step time follows the energy per cell-update)
 // No thread computes a global address for staging, no register holds one, and no plain load is left in the loop (the
 // nibble LDGs of the LDGSTS kernel cost a scoreboard wait per iteration).
 // Requirements (checked by the driver, which otherwise launches k_sweby_xy): even ni+2, 16-byte aligned bases.
@@ -45,9 +47,7 @@ struct FusedMaps {
 
 template <int NT, bool UPD>
 struct FusedTmaLayout {
-    // rows of FT_RW doubles.  Operands are staged TWO iterations ahead of their use (one iteration -- about 0.7 us -- is less than the
-    // loaded DRAM latency: with a distance of one the warps spent ~17% of their issue slots spinning on the `full` barrier), so the
-    // slots are: ring 5 (rows jf .. jf+4 are alive at once), x-only 3, y-only 3.
+    // rows of FT_RW doubles
     static constexpr int NR = NT + 4;                 // ring: T[NT], u, rho, dyte, datr
     static constexpr int R_U = NT, R_RHO = NT + 1, R_DYTE = NT + 2, R_DATR = NT + 3;
     static constexpr int NX = NT + 1;                 // x-only: tm[NT], dxte
@@ -55,11 +55,10 @@ struct FusedTmaLayout {
     static constexpr int NTH = UPD ? 0 : NT;          // th_tendency rows (the time-update flavour does not read th_tendency)
     static constexpr int NY = NTH + 5 + (UPD ? 2 : 0); // y-only: th[NTH], v, w(k-1), w(k), dxtn, dytn (+ rho_m1, rho_r)
     static constexpr int Y_V = NTH, Y_WM = NTH + 1, Y_WK = NTH + 2, Y_DXTN = NTH + 3, Y_DYTN = NTH + 4, Y_RM1 = NTH + 5, Y_RR = NTH + 6;
-    static constexpr int RING_SLOTS = 5, XY_SLOTS = 3;
-    static constexpr int ROWS = RING_SLOTS * NR + XY_SLOTS * NX + XY_SLOTS * NY;
+    static constexpr int ROWS = 4 * NR + 2 * NX + 2 * NY;
     static constexpr size_t NIB_OFF = (size_t)ROWS * FT_RW * sizeof(double);
-    static constexpr size_t BAR_OFF = NIB_OFF + 2 * XY_SLOTS * 256;  // nibx[3], niby[3]: 144-byte rows in 256-byte slots (128-byte aligned boxes)
-    static constexpr size_t BYTES = BAR_OFF + 2 * XY_SLOTS * sizeof(uint64_t); // full[3], done[3]
+    static constexpr size_t BAR_OFF = NIB_OFF + 4 * 256;            // nibx[2], niby[2]: 144-byte rows in 256-byte slots (128-byte aligned boxes)
+    static constexpr size_t BYTES = BAR_OFF + 4 * sizeof(uint64_t); // full[2], done[2]
 };
 
 template <int NT, int VAR, bool DIAG, bool UPD = false>
@@ -68,13 +67,13 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
 {
     typedef FusedTmaLayout<NT, UPD> LY;
     extern __shared__ __align__(128) double fsm[];
-    double *const ring = fsm;                                            // [5][NR][FT_RW]
-    double *const xs = ring + LY::RING_SLOTS * LY::NR * FT_RW;          // [3][NX][FT_RW]
-    double *const ys = xs + LY::XY_SLOTS * LY::NX * FT_RW;              // [3][NY][FT_RW]
-    uint8_t *const nbx_s = reinterpret_cast<uint8_t *>(fsm) + LY::NIB_OFF;   // [3][256]
-    uint8_t *const nby_s = nbx_s + LY::XY_SLOTS * 256;                       // [3][256]
-    uint64_t *const full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(fsm) + LY::BAR_OFF);   // [3]
-    uint64_t *const done = full + LY::XY_SLOTS;                                                            // [3]
+    double *const ring = fsm;                               // [4][NR][FT_RW]
+    double *const xs = ring + 4 * LY::NR * FT_RW;           // [2][NX][FT_RW]
+    double *const ys = xs + 2 * LY::NX * FT_RW;             // [2][NY][FT_RW]
+    uint8_t *const nbx_s = reinterpret_cast<uint8_t *>(fsm) + LY::NIB_OFF;   // [2][FT_NW]
+    uint8_t *const nby_s = nbx_s + 2 * 256;                                  // [2][256]
+    uint64_t *const full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(fsm) + LY::BAR_OFF);
+    uint64_t *const done = full + 2;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     // linear block id, k fastest (2-D metrics and w(k-1) of concurrently resident blocks hit in L2)
     const int lin = blockIdx.x;
@@ -84,8 +83,8 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
     const int jc = a.tile_first + (rest / nxb) * a.tile_step;
     const int nact = min(FWARPS, nxt - tile0);            // active warps (x tiles inside the domain), >= 1
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < LY::XY_SLOTS; q++) { mbar_init(&full[q], 1); mbar_init(&done[q], nact); }
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&done[0], nact); mbar_init(&done[1], nact);
         mbar_fence_init();
     }
     __syncthreads();
@@ -107,17 +106,14 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
     const int nsh = iw0 & 15;                             // a nibble row is fetched from the 16-byte boundary at or below the stretch
     const bool acc = !UPD && a.accumulate;
 
-    // ---- producer: fill number f = everything iteration f consumes: x-row jf0+f+2 (ring slot f5 = f % 5, x-only slot f3 = f % 3) and
-    // face row jf0+f (y-only slot f3); it signals full[f3] ----
+    // ---- producer: everything iteration `it` stages (consumed in iteration it + 1) ----
     constexpr unsigned ROWB = FT_RW * sizeof(double);
-    const int jf0 = js - 4;                               // first (warm-up) iteration: produces row js-2
-    auto issue = [&](int f, int f3, int f5) {
-        const int r1 = jf0 + f + 2;                       // row staged for the x phase of iteration f
-        const int f1 = jf0 + f;                           // face row staged for the y phase of iteration f
+    auto issue = [&](int jf, uint64_t *bar) {
+        const int r1 = jf + 3;                            // row staged for the x phase of the next iteration
+        const int f1 = jf + 1;                            // face row staged for the y phase of the next iteration
         const bool do_face = (f1 >= js - 1);
         const int kz = k - 1;                             // level index of the data-domain arrays
-        uint64_t *bar = &full[f3];
-        double *R = ring + f5 * (LY::NR * FT_RW), *X = xs + f3 * (LY::NX * FT_RW), *Y = ys + f3 * (LY::NY * FT_RW);
+        double *R = ring + (r1 & 3) * (LY::NR * FT_RW), *X = xs + (r1 & 1) * (LY::NX * FT_RW), *Y = ys + (f1 & 1) * (LY::NY * FT_RW);
         const unsigned rows_x = 2 * NT + 5;               // T, tm [NT each], u, rho, dyte, datr, dxte
         const unsigned rows_y = (acc ? NT : 0) + 5 + (UPD ? 2 : 0);
         mbar_expect_tx(bar, rows_x * ROWB + FT_NW + (do_face ? rows_y * ROWB + FT_NW : 0u));
@@ -130,7 +126,7 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
         tma_load_3d(R + LY::R_RHO * FT_RW, &maps.rho, iw0, r1, kz, bar);
         tma_load_3d(R + LY::R_DYTE * FT_RW, &maps.met_ring, iw0, r1, 0, bar);              // two planes: dyte, datr
         tma_load_3d(X + LY::X_DXTE * FT_RW, &maps.dxte, iw0, r1, 0, bar);
-        tma_load_3d(nbx_s + f3 * 256, &maps.nibx, iw0 - nsh, r1, kz, bar);
+        tma_load_3d(nbx_s + (r1 & 1) * 256, &maps.nibx, iw0 - nsh, r1, kz, bar);
         if (do_face) {
             if (acc) {
 #pragma unroll
@@ -143,19 +139,15 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
             tma_load_3d(Y + LY::Y_V * FT_RW, &maps.v, iw0, f1, kz, bar);
             tma_load_3d(Y + LY::Y_WM * FT_RW, &maps.w, iw0, f1, k - 1, bar);               // two levels: w(k-1), w(k) of (..,0:nk)
             tma_load_3d(Y + LY::Y_DXTN * FT_RW, &maps.met_y, iw0, f1, 0, bar);             // two planes: dxtn, dytn
-            tma_load_3d(nby_s + f3 * 256, &maps.niby, iw0 - nsh, f1, kz, bar);
+            tma_load_3d(nby_s + (f1 & 1) * 256, &maps.niby, iw0 - nsh, f1, kz, bar);
         }
     };
     auto row_x = [&](int r) { return r >= 1 && r <= g.nj; };       // rows the x sweep is evaluated on
 
-    const int nit = je - jf0 + 1;                                   // iterations of this chunk
-    // prologue: fills 0 and 1 (what iterations 0 and 1 consume)
+    const int jf0 = js - 4;                                         // first (warm-up) iteration: produces row js-2
+    // prologue: what iteration 0 consumes (row jf0+2; the face row jf0 is never used: jf0 < js-1)
     if (wy == 0) {
-        if (elect_one()) {
-            issue(0, 0, 0);
-            if (nit > 1) issue(1, 1, 1);
-        }
-        __syncwarp();
+        if (elect_one()) issue(jf0 - 1, &full[0]);
     }
     const unsigned nby_first = a.nib2[q0 + (ofs_t)(js - 1) * nxd];  // y nibble of the first face (initial differences)
 
@@ -170,8 +162,6 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
 
     int it = 0;                                                     // iteration counter; jf = jf0 + it
     int prod = 0;                                                   // producer warp of this iteration = it % nact
-    int m3 = 0, m5 = 0;                                             // it % 3, it % 5
-    unsigned ph3 = 0;                                               // (it / 3) & 1
     // One iteration of the march.  GEN = true is the general form; GEN = false is the steady state of a chunk that touches no
     // halo row of the x-updated tracer (rows js-2 .. je+2 inside 1..nj) once its warm-up is over: the x phase always runs, the y
     // phase always runs on a live cell -- the loop body is then free of data-independent branches (ncu: branch_resolving was
@@ -179,26 +169,22 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
     auto body = [&](const int jf, auto gen_tag) {
         constexpr bool GEN = decltype(gen_tag)::value;
         const int r = jf + 2;                                       // row produced by this iteration
-        // slots of this iteration: x-row r lives in ring slot m5 / x-only slot m3, face jf in y-only slot m3; the y phase reads the
-        // ring rows jf (slot m5-2) and jf+1 (slot m5-1); fill it+2 goes to slots m5+2 / m3+2 (all modulo 5 / 3)
-        const int m3p2 = m3 ? m3 - 1 : 2;                           // (it + 2) % 3 == (it - 1) % 3
-        const int m5p2 = m5 + 2 - (m5 >= 3 ? 5 : 0), m5m2 = m5 + 3 - (m5 >= 2 ? 5 : 0), m5m1 = m5 + 4 - (m5 >= 1 ? 5 : 0);
-        // ---- producer of this iteration: fill it+2, once every warp has finished iteration it-1 (the last reader of those slots) ----
-        if (it + 2 < nit && wy == prod) {                           // warp-uniform
+        // ---- producer of this iteration: stage row r+1 and face jf+1 once every warp has finished iteration it-1 ----
+        if (jf < je && wy == prod) {                                // warp-uniform
             if (elect_one()) {
-                if (it >= 1) mbar_wait(&done[m3p2], ph3 ^ (m3 == 0 ? 1u : 0u));   // done(it-1): barrier (it-1)%3, parity ((it-1)/3)&1
-                issue(it + 2, m3p2, m5p2);
+                if (it >= 1) mbar_wait(&done[(it - 1) & 1], (unsigned)((it - 1) >> 1) & 1u);
+                issue(jf, &full[(it + 1) & 1]);
             }
             __syncwarp();
         }
         if (++prod == nact) prod = 0;
-        // ---- operands of this iteration: fill number `it` (issued during iteration it-2; the prologue issued fills 0 and 1) ----
-        mbar_wait(&full[m3], ph3);
+        // ---- operands of this iteration: fill number `it` (issued during iteration it-1; the prologue is fill 0) ----
+        mbar_wait(&full[it & 1], (unsigned)(it >> 1) & 1u);
 
         // ---------------- x: produce tm(i, r, k) -> L.t2 ----------------
         if (!GEN || row_x(r)) {
-            const double *R = ring + m5 * (LY::NR * FT_RW), *X = xs + m3 * (LY::NX * FT_RW);
-            const unsigned nbx = nbx_s[m3 * 256 + col + nsh];
+            const double *R = ring + (r & 3) * (LY::NR * FT_RW), *X = xs + (r & 1) * (LY::NX * FT_RW);
+            const unsigned nbx = nbx_s[(r & 1) * 256 + col + nsh];
             F.nb = nbx;
             F.dyte = R[LY::R_DYTE * FT_RW + col];
             F.dxte = X[LY::X_DXTE * FT_RW + col];
@@ -249,10 +235,10 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
 
         if (!GEN || jf >= js - 1) {
             // ---------------- y: north face jf and (when live) cell (i, jf, k) ----------------
-            const double *R = ring + m5m2 * (LY::NR * FT_RW), *R1 = ring + m5m1 * (LY::NR * FT_RW);
-            const double *Y = ys + m3 * (LY::NY * FT_RW);
+            const double *R = ring + (jf & 3) * (LY::NR * FT_RW), *R1 = ring + ((jf + 1) & 3) * (LY::NR * FT_RW);
+            const double *Y = ys + (jf & 1) * (LY::NY * FT_RW);
             if (GEN && jf == js - 1) L.rho0 = R[LY::R_RHO * FT_RW + col];
-            L.nb = nby_s[m3 * 256 + col + nsh];
+            L.nb = nby_s[(jf & 1) * 256 + col + nsh];
             L.live = GEN ? (jf >= js) : 1;
             L.vv = Y[LY::Y_V * FT_RW + col];
             L.rho1 = R1[LY::R_RHO * FT_RW + col];
@@ -306,10 +292,8 @@ k_sweby_xy_tma(const Geom g, const SwebyArgs<NT> a, const __grid_constant__ Fuse
         for (int n = 0; n < NT; n++) { L.t0[n] = L.t1[n]; L.t1[n] = L.t2[n]; }
         // ---- end of iteration: every value read from the staging slots has been consumed ----
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[m3]);
+        if (lane == 0) mbar_arrive(&done[it & 1]);
         it++;
-        if (++m3 == 3) { m3 = 0; ph3 ^= 1u; }
-        if (++m5 == 5) m5 = 0;
     };
     int jf = jf0;
 #ifdef FT_PEEL   // measured on B200 (profiles/ab_r02_j_*.json): the specialised steady-state body costs 10 registers and is 2% SLOWER

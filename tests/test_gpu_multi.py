@@ -58,6 +58,9 @@ def _worker(rank, world, port, cases, outdir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    # ONE CPU thread per worker: the blocks are generated with torch on the host, and N workers each spinning up a thread per core
+    # oversubscribe the box (measured on a 4-GPU box: 130 s per case instead of 0.3 s)
+    torch.set_num_threads(1)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from mom5_b200.api import ADVECT_MDFL_SWEBY, ADVECT_MDFL_SWEBY_TEST, ADVECT_MDPPM, ADVECT_QUICKER, Communicator, TracerAdvect
@@ -146,7 +149,8 @@ def _run_world(tmp_path, world):
     cases = CASES[world]
     if os.environ.get("MOM5_MULTI_QUICK"):     # development runs: only the wide cases that reach the overlap branches
         cases = [c for c in cases if c[1].get("ni", 0) >= 994]
-    saved = {k: os.environ.get(k) for k in ("MOM5ADV_FUSE", "MOM5ADV_TMA")}
+    saved = {k: os.environ.get(k) for k in ("MOM5ADV_FUSE", "MOM5ADV_TMA", "OMP_NUM_THREADS")}
+    os.environ["OMP_NUM_THREADS"] = "1"        # inherited by the spawned workers (see _worker)
     try:
         mp.spawn(_worker, args=(world, _free_port(), cases, str(tmp_path)), nprocs=world, join=True)
     finally:

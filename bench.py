@@ -71,11 +71,12 @@ def measured_peaks():
 
 
 def kernel_source_hash() -> str:
-    """hash of the CUDA sources: a traffic file measured on other kernels is refused"""
+    """hash of the kernel sources (csrc/*.cuh: every kernel of the hot path lives in a header; capi.cu is the host driver):
+    a traffic file measured on other kernels is refused"""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "mom5_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
+        if f.endswith(".cuh"):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

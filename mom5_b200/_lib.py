@@ -58,6 +58,7 @@ SYMBOLS = {
 DEBUG_SYMBOLS = {
     "mom5adv_debug_plan": (C.c_int, [C.c_int] * 10 + [ip, C.c_int]),
     "mom5adv_debug_extent": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
+    "mom5adv_debug_overlap_sets": (C.c_int, [C.c_int, C.c_int, C.c_int, ip]),
 }
 
 _lib = None

@@ -969,27 +969,75 @@ static int z_tiles(int ni) { return (ni + ZBX) / ZBX; }
 // comm/compute overlap: everything the strip pack reads, and every tile that reads what the strip unpack writes.
 static int edge_tiles(int n, int size, int nt) { return (n - (nt - 1) * size >= 2 || nt < 2) ? 1 : 2; }
 
+static int f_rows_for(int ni, int nj, int nk)
+{   // rows per j-chunk of the fused pass: every chunk redoes the x arithmetic of 4 rows, so as large as >= ~4 waves of blocks allow
+    const int nxt = (ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
+    int rows = FROWS_MAX;
+    while (rows > 8 && (long long)nk * nxb * ((nj + rows - 1) / rows) < 148LL * FMINB * 4) rows /= 2;
+    return rows;
+}
+static void pick_f_rows(mom5adv_ctx *h) { h->f_rows = f_rows_for(h->g.ni, h->g.nj, h->g.nk); }
+
+static int y_rows_for(int ni, int nj, int nk)
+{   // y-sweep chunking of the three-sweep driver (rows per j-chunk): >= ~4 waves of threads, at most YROWS_MAX rows
+    const int YBX = 32 * YWARPS;
+    const long long per_chunk = (long long)((ni + YBX - 1) / YBX) * YBX * nk;
+    int rows = YROWS_MAX;
+    while (rows > 8 && per_chunk * ((nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
+    return rows;
+}
+
+// The tile sets of the comm/compute overlap, as pure functions of the block shape (mom5adv_debug_overlap_sets exposes them to the
+// CPU tests, which check the two invariants the overlap rests on for thousands of shapes: every cell a strip PACK reads has been
+// produced by an edge tile, and no interior tile reads a cell a strip UNPACK writes).
+struct OverlapSets {
+    int nzt, z_last;            // z tiles; trailing tiles in the edge set (tile 0 always is)
+    int f_rows, njc_f, c_hi;    // fused pass: rows per chunk, chunks, interior chunks are 1..c_hi
+    int nxt, x_last;            // three-sweep driver, x tiles of 31 cells
+    int y_rows, njc_y, y_last;  // three-sweep driver, y chunks
+};
+static OverlapSets overlap_sets(int ni, int nj, int nk)
+{
+    OverlapSets o;
+    o.nzt = z_tiles(ni);
+    // the last two columns span two tiles when ni % ZBX == 0: z tile t covers the data-domain columns t*ZBX .. t*ZBX + ZBX-1
+    o.z_last = (ni - (o.nzt - 1) * ZBX + 1 >= 2 || o.nzt < 2) ? 1 : 2;
+    o.f_rows = f_rows_for(ni, nj, nk);
+    o.njc_f = (nj + o.f_rows - 1) / o.f_rows;
+    // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
+    o.c_hi = std::min((nj - 2) / o.f_rows - 1, o.njc_f - 1);
+    o.nxt = (ni + 30) / 31;
+    o.x_last = edge_tiles(ni, 31, o.nxt);
+    o.y_rows = y_rows_for(ni, nj, nk);
+    o.njc_y = (nj + o.y_rows - 1) / o.y_rows;
+    o.y_last = edge_tiles(nj, o.y_rows, o.njc_y);
+    return o;
+}
+
+extern "C" int mom5adv_debug_overlap_sets(int ni, int nj, int nk, int out[12])
+{
+    if (ni < 1 || nj < 1 || nk < 1 || !out) { set_error("mom5adv_debug_overlap_sets: bad arguments"); return MOM5ADV_EINVAL; }
+    const OverlapSets o = overlap_sets(ni, nj, nk);
+    const int v[12] = {o.nzt, o.z_last, o.f_rows, o.njc_f, o.c_hi, o.nxt, o.x_last, o.y_rows, o.njc_y, o.y_last, ZBX, 31};
+    for (int q = 0; q < 12; q++) out[q] = v[q];
+    return 0;
+}
+
 // Three separate sweeps (z, x, y), the running tracer materialised between them as the reference does.
 static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
     int rc;
     const Geom &g = h->g;
-    // y-sweep chunking (rows per j-chunk): >= ~4 waves of threads, at most 32 rows
-    {
-        const int YBX = 32 * YWARPS;
-        const long long per_chunk = (long long)((g.ni + YBX - 1) / YBX) * YBX * g.nk;
-        int rows = YROWS_MAX;
-        while (rows > 8 && per_chunk * ((g.nj + rows - 1) / rows) < 148LL * 2048 * 2) rows /= 2;
-        h->y_rows = rows;
-    }
-    const int nxt = (g.ni + 30) / 31, njc = (g.nj + h->y_rows - 1) / h->y_rows;
+    const OverlapSets os = overlap_sets(g.ni, g.nj, g.nk);
+    h->y_rows = os.y_rows;
+    const int nxt = os.nxt, njc = os.njc_y;
     // Overlap the NCCL strip exchange with the interior tiles of the sweep that consumes it (the reference's only
     // overlap is tracer n's exchange with tracer n+1's compute, OTA:4214-4216): the exchange runs on the library's comm
-    // stream while the x (y) sweep works on the tiles (j-chunks) that read no halo; the two edge tiles follow.
+    // stream while the x (y) sweep works on the tiles (j-chunks) that read no halo; the edge tiles follow.
     // The tiles that run under the exchange must touch no halo cell (the unpack writes them concurrently): x tile t reads
     // tm(31t-1 .. 31t+33), y chunk c reads rows cR-1 .. (c+1)R+2.  When the last tile (chunk) holds a single column (row)
     // the one before it reaches into the halo as well and joins the edge set.
-    const int x_last = edge_tiles(g.ni, 31, nxt), y_last = edge_tiles(g.nj, h->y_rows, njc);
+    const int x_last = os.x_last, y_last = os.y_last;
     const bool ovx = h->overlap && plan_has_remote(h, 1) && nxt >= 3 + x_last;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && njc >= 3 + y_last;
     cudaStream_t sc = h->s_comm;
@@ -1035,15 +1083,6 @@ static int sweby_dev_unfused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st
     return 0;
 }
 
-static void pick_f_rows(mom5adv_ctx *h)
-{   // rows per j-chunk of the fused pass: every chunk redoes the x arithmetic of 4 rows, so as large as >= ~4 waves of blocks allow
-    const Geom &g = h->g;
-    const int nxt = (g.ni + 30) / 31, nxb = (nxt + FWARPS - 1) / FWARPS;
-    int rows = FROWS_MAX;
-    while (rows > 8 && (long long)g.nk * nxb * ((g.nj + rows - 1) / rows) < 148LL * FMINB * 4) rows /= 2;
-    h->f_rows = rows;
-}
-
 // z sweep, then x and y in one pass (k_sweby_xy): the x-updated tracer exists in HBM only on the four edge rows whose
 // north/south halo images the fused pass reads back.  With remote neighbours the work is spread over three streams so that
 // neither the exchanges nor the small edge launches sit on the critical path:
@@ -1056,15 +1095,13 @@ static int sweby_dev_fused(mom5adv_ctx *h, const SwebyCall &c, cudaStream_t st)
 {
     int rc;
     const Geom &g = h->g;
-    pick_f_rows(h);
-    const int rows = h->f_rows, njc = (g.nj + rows - 1) / rows;
-    const int nzt = z_tiles(g.ni);
-    // chunks jc in [1, c_hi] read no halo row of the x-updated tracer (rows js-2 .. je+2 lie inside 1..nj)
-    const int c_hi = std::min((g.nj - 2) / rows - 1, njc - 1);
+    const OverlapSets os = overlap_sets(g.ni, g.nj, g.nk);
+    h->f_rows = os.f_rows;
+    const int njc = os.njc_f, nzt = os.nzt;
+    // chunks jc in [1, c_hi] read no halo row of the x-updated tracer; the z tiles holding the columns 1, 2, ni-1, ni the E/W strip
+    // pack reads (tile 0 and the last z_last tiles) run BEFORE the exchange starts (overlap_sets)
+    const int c_hi = os.c_hi, z_last = os.z_last;
     const bool need_y = !h->plan[2].recvs.empty();
-    // z tiles holding the columns 1, 2, ni-1, ni the E/W strip pack reads run BEFORE the exchange starts (the last two
-    // columns span two tiles when ni % ZBX == 0: z tile t covers the data-domain columns t*ZBX .. t*ZBX + ZBX-1)
-    const int z_last = (g.ni - (nzt - 1) * ZBX + 1 >= 2 || nzt < 2) ? 1 : 2;
     const bool ovx = h->overlap && plan_has_remote(h, 1) && nzt >= 3 + z_last;
     const bool ovy = h->overlap && plan_has_remote(h, 2) && c_hi >= 1;
     cudaStream_t sc = h->s_comm, se = h->s_edge;

@@ -119,3 +119,42 @@ def test_plan_execution_equals_oracle_update(cfg, flags, halo):
     orc.lib().orc_update_halo(C.byref(lay), orc._pp(b), nk, halo, flags)
     for r in range(dec.nranks):
         assert np.array_equal(a[r], b[r]), f"rank {r}"
+
+
+def test_overlap_edge_sets_cover_every_cell_a_strip_touches():
+    """The comm/compute overlap of both Sweby drivers rests on two invariants (round-1 advisor finding: with ni_local = 513 the E/W pack
+    could read a column of an interior z tile that had not run yet):
+      (1) every cell a strip PACK reads was produced by a tile of the edge set, which runs before the exchange starts;
+      (2) no tile that runs UNDER the exchange reads a cell the strip UNPACK writes.
+    Checked on the library's own tile sets (mom5adv_debug_overlap_sets, the very function the drivers call) for every block
+    width / height up to 1100 plus the bench shapes."""
+    import ctypes as C
+    from mom5_b200 import _lib
+    L = _lib.load()
+    out = (C.c_int * 12)()
+
+    def sets(ni, nj, nk):
+        assert L.mom5adv_debug_overlap_sets(ni, nj, nk, out) == 0
+        return list(out)
+
+    shapes = [(n, 80, 6) for n in range(2, 1101)] + [(520, n, 6) for n in range(2, 1101)] + \
+             [(3600, 2700, 75), (1800, 675, 75), (1800, 1350, 75), (1800, 2700, 75), (513, 41, 6), (497, 80, 6), (720, 540, 50)]
+    for ni, nj, nk in shapes:
+        nzt, z_last, f_rows, njc_f, c_hi, nxt, x_last, y_rows, njc_y, y_last, zbx, xw = sets(ni, nj, nk)
+        # ---- z tiles: tile t = data-domain columns t*zbx .. t*zbx + zbx-1; the E/W pack reads columns 1, 2, ni-1, ni
+        assert nzt == ni // zbx + 1
+        edge_z = {0} | set(range(nzt - z_last, nzt))
+        for col in (1, min(2, ni), max(ni - 1, 1), ni):
+            assert col // zbx in edge_z, (ni, col, "z edge set")
+        # ---- fused pass: interior chunks 1..c_hi read rows js-2 .. je+2 with js = jc*R+1, je = (jc+1)*R: none may be a halo row
+        for jc in range(1, c_hi + 1):
+            js, je = jc * f_rows + 1, min((jc + 1) * f_rows, nj)
+            assert js - 2 >= 1 and je + 2 <= nj, (nj, f_rows, jc, "fused interior chunk reads a halo row")
+        assert c_hi <= njc_f - 1
+        # ---- three-sweep driver, x: interior tiles 1 .. nxt-1-x_last read tm(31t-1 .. 31t+33)
+        assert nxt == (ni + 30) // 31
+        for t in range(1, nxt - x_last):
+            assert xw * t - 1 >= 1 and xw * t + 33 <= ni, (ni, t, "x interior tile reads a halo column")
+        # ---- three-sweep driver, y: interior chunks 1 .. njc_y-1-y_last read rows cR-1 .. (c+1)R+2
+        for c in range(1, njc_y - y_last):
+            assert c * y_rows - 1 >= 1 and (c + 1) * y_rows + 2 <= nj, (nj, y_rows, c, "y interior chunk reads a halo row")

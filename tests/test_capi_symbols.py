@@ -34,6 +34,16 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(_lib.SYMBOLS) == names
 
 
+def test_fma_tolerance_build_exports_the_same_symbols():
+    """libmom5adv_fma.so (the FMA-contracted tolerance build one GPU test loads in a subprocess) must be as current as the bit-exact
+    library: same exported entry points, test hooks included (a stale build shows up here, on the CPU)"""
+    from mom5_b200 import build
+    path = build.build(fma=True)                      # rebuilds when a source is newer
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+    for nm in list(_lib.SYMBOLS) + list(_lib.DEBUG_SYMBOLS):
+        assert hasattr(lib, nm), f"{nm} missing from {path}"
+
+
 def test_no_link_time_dependency_on_nccl_or_torch():
     """NCCL is dlopen'ed on first use so that a host process keeps its own copy (PyTorch bundles one)."""
     import subprocess

@@ -1,5 +1,6 @@
 // tma_probe.cu -- which (box, origin) combinations of an FP64 tensor-map copy does this GPU accept?  (diagnostic; run on the GPU box)
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe tma_probe.cu ; ./tma_probe NX NY NZ B0 B1 B2 C0 C1 C2
+//   (the binary is built here and travels to the GPU box with the snapshot; it is git-ignored.  Results: profiles/tma_probe_r02.log)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -451,7 +451,7 @@ def release(keep):
     torch.cuda.empty_cache()
 
 
-def traffic_record(kname):
+def traffic_record(kname, cells=None, ntr=None):
     """ncu --set full DRAM bytes per launch of `kname` at the bench workload, from this round's profile file -- refused when the
     file was measured on different kernel sources"""
     p = os.path.join(ROOT, "profiles", f"traffic_{ROUND}.json")
@@ -463,7 +463,15 @@ def traffic_record(kname):
         return None, f"unreadable: {ex}"
     if d.get("kernel_source_sha1") != kernel_source_hash():
         return None, f"stale: measured on sources {d.get('kernel_source_sha1')}, current {kernel_source_hash()}"
-    return d.get("kernels", {}).get(kname), "ncu --set full, " + d.get("source", "")
+    t = d.get("kernels", {}).get(kname)
+    src = "ncu --set full, " + d.get("source", "")
+    if t is not None and cells and ntr and d.get("cells_per_launch"):
+        if ntr != d.get("tracers", ntr):
+            return None, f"measured with {d.get('tracers')} tracers, this run has {ntr}"
+        if cells != d["cells_per_launch"]:      # a smaller block per GPU: the streaming traffic of a launch scales with its cells
+            t = t * cells / d["cells_per_launch"]
+            src = f"scaled by cells per launch ({cells} / {d['cells_per_launch']}) from: " + src
+    return t, src
 
 
 def config2_extras(env):
@@ -566,7 +574,7 @@ def run_gpu(args):
     kname = kernels[dom]
     dom_ms = max(phase[phase_of[dom]], 1e-9)
     ach = cells * sb[dom] / (dom_ms * 1e-3) / 1e9
-    traffic, traffic_src = traffic_record(kname)
+    traffic, traffic_src = traffic_record(kname, cells, ntr)
     roofline = dict(bound="hbm", kernel=kname, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
                     traffic_source=traffic_src, peak_source=peak_src,
                     per_sweep={k: dict(kernel=kernels[k], ms=phase[phase_of[k]], alg_bytes_per_cell=sb[k],
